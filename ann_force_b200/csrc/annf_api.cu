@@ -1,0 +1,512 @@
+// C-ABI of libannforce_b200 (declared in include/annforce_b200.h): handle life-cycle, parameter
+// upload, kernel selection and the launchers.  No exceptions cross this boundary and there is no
+// CPU fallback: without a CUDA device every entry point fails with ANNF_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "annf_common.cuh"
+#include "annf_profiler.h"
+
+namespace annf {
+// annf_single.cu
+size_t single_smem_bytes(const NetView& net);
+cudaError_t prepare_single(const NetView& net, int cluster_size);
+cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq, const void* posq_corr,
+                          unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream);
+// annf_batched.cu
+size_t batched_smem_bytes(const NetView& net, int extra_nodes, int tr, bool fp64);
+cudaError_t launch_batched(const NetView& net, const int* x_off, int extra_nodes, int tr, bool fp64, int R,
+                           const float* coords, int atoms_per_replica, const float* centers, float* forces,
+                           double* energies, cudaStream_t stream);
+// annf_tensor.cu
+struct TensorPlan;
+TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, std::string* why_not);
+void tensor_plan_destroy(TensorPlan* plan);
+cudaError_t tensor_plan_run(TensorPlan* plan, Profiler* prof, const NetView& net, int R,
+                            const float* coords, int atoms_per_replica, const float* centers, float* forces,
+                            double* energies, cudaStream_t stream, long long* launches);
+}  // namespace annf
+
+using namespace annf;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+annf_status fail(annf_status code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define ANNF_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess)                                                                    \
+            return fail(ANNF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+cudaError_t upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    const size_t bytes = sizeof(T) * std::max<size_t>(src.size(), 1);
+    cudaError_t err = cudaMalloc((void**) dst, bytes);
+    if (err != cudaSuccess) return err;
+    if (!src.empty()) err = cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+    return err;
+}
+
+__global__ void invert_order_kernel(const int* __restrict__ atom_index, int num_atoms, int* __restrict__ inverse) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < num_atoms) inverse[atom_index[slot]] = slot;
+}
+
+__global__ void remap_kernel(const int* __restrict__ atoms, int n, const int* __restrict__ inverse, int* __restrict__ slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slots[i] = inverse[atoms[i]];
+}
+
+__global__ void set_parameters_kernel(double* center, const double* staged, int n, double* k_dev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) center[i] = staged[i];
+    if (i == 0) *k_dev = staged[n];
+}
+
+}  // namespace
+
+struct annf_context {
+    int device = 0;
+    int sm_count = 0;
+    NetView net{};
+    std::vector<int> nodes, types;
+    int num_system_atoms = 0;
+    long long macs = 0;
+    int prec_single = ANNF_PREC_FP64, prec_batched = ANNF_PREC_FP64;
+    int batched_path = 0;
+    int cluster_size = 1;
+    int tile_fp64 = 1, tile_fp32 = 1;
+    int x_off[kMaxLayers];
+    int extra_nodes = 0;
+    long long launches = 0;
+    // device allocations
+    double *W64 = nullptr, *Wt64 = nullptr, *b64 = nullptr, *center = nullptr, *k_dev = nullptr, *staged = nullptr;
+    float *W32 = nullptr, *Wt32 = nullptr, *b32 = nullptr;
+    int *sel_atoms = nullptr, *sel_slots = nullptr, *inverse = nullptr;
+    double* staged_host = nullptr;   // pinned, [num_center + 1]
+    TensorPlan* tensor = nullptr;
+    Profiler prof;
+    // host-buffer entry
+    cudaStream_t host_stream = nullptr;
+    float *h_coords = nullptr, *h_centers = nullptr, *h_forces = nullptr;
+    double* h_energies = nullptr;
+    size_t h_cap_coords = 0, h_cap_centers = 0, h_cap_energies = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int previous = -1;
+    explicit DeviceGuard(int device) {
+        cudaGetDevice(&previous);
+        if (previous != device) cudaSetDevice(device);
+        else previous = -1;
+    }
+    ~DeviceGuard() { if (previous >= 0) cudaSetDevice(previous); }
+};
+
+void release(annf_context* h) {
+    DeviceGuard guard(h->device);
+    h->prof.drain();
+    if (h->tensor) tensor_plan_destroy(h->tensor);
+    cudaFree(h->W64); cudaFree(h->Wt64); cudaFree(h->b64); cudaFree(h->center); cudaFree(h->k_dev); cudaFree(h->staged);
+    cudaFree(h->W32); cudaFree(h->Wt32); cudaFree(h->b32);
+    cudaFree(h->sel_atoms); cudaFree(h->sel_slots); cudaFree(h->inverse);
+    cudaFree(h->h_coords); cudaFree(h->h_centers); cudaFree(h->h_forces); cudaFree(h->h_energies);
+    if (h->staged_host) cudaFreeHost(h->staged_host);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* annf_version(void) { return "annforce_b200 0.1 (sm_100a, abi 1)"; }
+
+const char* annf_last_error(void) { return g_last_error.c_str(); }
+
+int annf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+annf_status annf_create(const annf_desc* desc, annf_handle* out) {
+    if (out == nullptr) return fail(ANNF_ERR_INVALID, "annf_create: out is NULL");
+    *out = nullptr;
+    if (desc == nullptr || desc->struct_size != sizeof(annf_desc))
+        return fail(ANNF_ERR_INVALID, "annf_create: descriptor missing or built against another ABI (struct_size %u, expected %zu)",
+                    desc ? desc->struct_size : 0u, sizeof(annf_desc));
+    const int L = desc->num_layers;
+    if (L < 2 || L > ANNF_MAX_LAYERS)
+        return fail(ANNF_ERR_INVALID, "num_layers = %d, supported range is 2..%d", L, ANNF_MAX_LAYERS);
+    if (!desc->num_of_nodes || !desc->layer_types || !desc->coeff || !desc->bias || !desc->potential_center)
+        return fail(ANNF_ERR_INVALID, "annf_create: NULL array in descriptor");
+    for (int l = 0; l < L; l++)
+        if (desc->num_of_nodes[l] <= 0) return fail(ANNF_ERR_INVALID, "num_of_nodes[%d] = %d", l, desc->num_of_nodes[l]);
+    for (int l = 0; l + 1 < L; l++) {
+        const int t = desc->layer_types[l];
+        if (t < ANNF_LINEAR || t > ANNF_SOFTMAX) return fail(ANNF_ERR_INVALID, "layer_types[%d] = %d is not a layer type", l, t);
+        if (t == ANNF_CIRCULAR && desc->num_of_nodes[l + 1] % 2 != 0)
+            return fail(ANNF_ERR_INVALID, "Circular layer %d needs an even number of nodes", l + 1);   // ANN_ReferenceKernels.cpp:211
+        if (!desc->coeff[l] || !desc->bias[l]) return fail(ANNF_ERR_INVALID, "coeff[%d] / bias[%d] is NULL", l, l);
+    }
+    const int n_last = desc->num_of_nodes[L - 1];
+    const int want_center = desc->layer_types[L - 2] == ANNF_CIRCULAR ? n_last / 2 : n_last;   // ANN_ReferenceKernels.cpp:61-66
+    if (desc->num_center != want_center)
+        return fail(ANNF_ERR_INVALID, "potential_center has %d values, the output layer needs %d", desc->num_center, want_center);
+    if (desc->scaling_factor == 0.0 || !std::isfinite(desc->scaling_factor))
+        return fail(ANNF_ERR_INVALID, "scaling_factor must be finite and non-zero");
+    if (desc->num_system_atoms <= 0) return fail(ANNF_ERR_INVALID, "num_system_atoms must be positive");
+    if (desc->data_type_in_input_layer == ANNF_INPUT_CARTESIAN) {
+        if (desc->num_backbone_atoms <= 0 || 3 * desc->num_backbone_atoms != desc->num_of_nodes[0])
+            return fail(ANNF_ERR_INVALID, "Cartesian input: 3 * %d selected atoms != %d input nodes",
+                        desc->num_backbone_atoms, desc->num_of_nodes[0]);                          // CudaANN_Kernels.cpp:188
+        for (int i = 0; i < desc->num_backbone_atoms; i++) {
+            const int a = desc->index_of_backbone_atoms[i];
+            if (a < 1 || a > desc->num_system_atoms)
+                return fail(ANNF_ERR_INVALID, "index_of_backbone_atoms[%d] = %d is outside 1..%d (indices are 1-based)", i, a,
+                            desc->num_system_atoms);
+        }
+    } else if (desc->data_type_in_input_layer == ANNF_INPUT_DIHEDRAL_COS_SIN ||
+               desc->data_type_in_input_layer == ANNF_INPUT_PAIR_DISTANCES) {
+        // The legacy CUDA kernel threw for dihedral input as well (CudaANN_Kernels.cpp:257-260).
+        return fail(ANNF_ERR_UNSUPPORTED, "data_type_in_input_layer = %d is not implemented on the CUDA path yet (Cartesian = 1 is)",
+                    desc->data_type_in_input_layer);
+    } else {
+        return fail(ANNF_ERR_INVALID, "data_type_in_input_layer = %d", desc->data_type_in_input_layer);
+    }
+    if (desc->precision < ANNF_PREC_AUTO || desc->precision > ANNF_PREC_TF32X3)
+        return fail(ANNF_ERR_INVALID, "precision = %d", desc->precision);
+
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(ANNF_ERR_NO_DEVICE, "no CUDA device is available; this library has no CPU fallback");
+    }
+    int device = desc->device;
+    if (device < 0) ANNF_CUDA(cudaGetDevice(&device));
+    if (device >= count) return fail(ANNF_ERR_INVALID, "device %d requested, %d present", device, count);
+    cudaDeviceProp prop;
+    ANNF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ANNF_ERR_UNSUPPORTED, "device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+
+    annf_context* h = new (std::nothrow) annf_context();
+    if (!h) return fail(ANNF_ERR_INVALID, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->num_system_atoms = desc->num_system_atoms;
+    DeviceGuard guard(device);
+
+    // ---- flatten the network --------------------------------------------------------------------------
+    NetView& net = h->net;
+    net.L = L;
+    std::vector<double> W64, Wt64, b64;
+    std::vector<std::vector<double>> coeff_rows;
+    net.node_off[0] = 0;
+    for (int l = 0; l < L; l++) {
+        net.nodes[l] = desc->num_of_nodes[l];
+        net.node_off[l + 1] = net.node_off[l] + net.nodes[l];
+        h->nodes.push_back(net.nodes[l]);
+    }
+    for (int l = 0; l + 1 < L; l++) {
+        const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+        net.types[l] = desc->layer_types[l];
+        h->types.push_back(net.types[l]);
+        net.w_off[l] = (long long) W64.size();
+        net.b_off[l] = (int) b64.size();
+        h->macs += (long long) n_in * n_out;
+        const double* w = desc->coeff[l];
+        for (size_t t = 0; t < (size_t) n_in * n_out; t++)
+            if (!std::isfinite(w[t])) { delete h; return fail(ANNF_ERR_INVALID, "coeff[%d][%zu] is not finite", l, t); }
+        W64.insert(W64.end(), w, w + (size_t) n_in * n_out);
+        Wt64.resize(W64.size());
+        double* wt = Wt64.data() + net.w_off[l];
+        for (int j = 0; j < n_out; j++)
+            for (int i = 0; i < n_in; i++) wt[(size_t) i * n_out + j] = w[(size_t) j * n_in + i];
+        b64.insert(b64.end(), desc->bias[l], desc->bias[l] + n_out);
+        coeff_rows.emplace_back(w, w + (size_t) n_in * n_out);
+    }
+    std::vector<float> W32(W64.begin(), W64.end()), Wt32(Wt64.begin(), Wt64.end()), b32(b64.begin(), b64.end());
+    std::vector<double> center(desc->potential_center, desc->potential_center + desc->num_center);
+    std::vector<double> kvec(1, desc->force_constant);
+    std::vector<int> sel(desc->num_backbone_atoms);
+    for (int i = 0; i < desc->num_backbone_atoms; i++) sel[i] = desc->index_of_backbone_atoms[i] - 1;   // ANN_ReferenceKernels.cpp:132
+
+#define ANNF_CUDA_H(call)                                                                            \
+    do {                                                                                             \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess) {                                                                  \
+            release(h);                                                                              \
+            return fail(ANNF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+        }                                                                                            \
+    } while (0)
+
+    ANNF_CUDA_H(upload(&h->W64, W64));
+    ANNF_CUDA_H(upload(&h->Wt64, Wt64));
+    ANNF_CUDA_H(upload(&h->b64, b64));
+    ANNF_CUDA_H(upload(&h->W32, W32));
+    ANNF_CUDA_H(upload(&h->Wt32, Wt32));
+    ANNF_CUDA_H(upload(&h->b32, b32));
+    ANNF_CUDA_H(upload(&h->center, center));
+    ANNF_CUDA_H(upload(&h->k_dev, kvec));
+    ANNF_CUDA_H(upload(&h->sel_atoms, sel));
+    ANNF_CUDA_H(upload(&h->sel_slots, sel));
+    ANNF_CUDA_H(cudaMalloc((void**) &h->inverse, sizeof(int) * h->num_system_atoms));
+    ANNF_CUDA_H(cudaMalloc((void**) &h->staged, sizeof(double) * (desc->num_center + 1)));
+    ANNF_CUDA_H(cudaMallocHost((void**) &h->staged_host, sizeof(double) * (desc->num_center + 1)));
+    net.W64 = h->W64; net.Wt64 = h->Wt64; net.b64 = h->b64;
+    net.W32 = h->W32; net.Wt32 = h->Wt32; net.b32 = h->b32;
+    net.center = h->center; net.k_dev = h->k_dev; net.num_center = desc->num_center;
+    net.scale = desc->scaling_factor;
+    net.input_type = desc->data_type_in_input_layer;
+    net.n_sel = desc->num_backbone_atoms;
+    net.sel_atoms = h->sel_atoms; net.sel_slots = h->sel_slots;
+    net.n_pairs = 0; net.pairs = nullptr; net.pair_slots = nullptr;
+    net.n_dihedrals = 0; net.dihedrals = nullptr; net.dihedral_slots = nullptr;
+
+    // ---- kernel selection ---------------------------------------------------------------------------------
+    // single replica: fp64 always (latency-bound; B200 fp64 FMA is half rate, parity is ~1e-12)
+    h->prec_single = ANNF_PREC_FP64;
+    const double weight_bytes = 8.0 * (double) h->macs;
+    int cl = 1;
+    while (cl < 8 && weight_bytes / cl > 48.0 * 1024) cl *= 2;
+    h->cluster_size = cl;
+    if (single_smem_bytes(net) > 227 * 1024) {
+        release(h);
+        return fail(ANNF_ERR_UNSUPPORTED, "network too large for the single-replica kernel's shared memory (%zu bytes)",
+                    single_smem_bytes(net));
+    }
+    ANNF_CUDA_H(prepare_single(net, cl));
+
+    // batched: extra shared-memory slots for non-elementwise hidden layers
+    h->extra_nodes = 0;
+    for (int l = 0; l < kMaxLayers; l++) h->x_off[l] = -1;
+    for (int l = 1; l + 1 < L; l++) {
+        const int t = net.types[l - 1];
+        if (t == ANNF_CIRCULAR || t == ANNF_SOFTMAX) {
+            h->x_off[l] = h->extra_nodes;
+            h->extra_nodes += 2 * net.nodes[l];
+        }
+    }
+    auto pick_tile = [&](bool fp64) {
+        for (int tr : {8, 4, 2, 1})
+            if (batched_smem_bytes(net, h->extra_nodes, tr, fp64) <= 200 * 1024) return tr;
+        return 0;
+    };
+    h->tile_fp64 = pick_tile(true);
+    h->tile_fp32 = pick_tile(false);
+    int prec = desc->precision;
+    std::string why_not;
+    if (prec == ANNF_PREC_AUTO || prec == ANNF_PREC_TF32X3) {
+        h->tensor = tensor_plan_create(net, coeff_rows, &why_not);
+        if (h->tensor == nullptr && prec == ANNF_PREC_TF32X3) {
+            release(h);
+            return fail(ANNF_ERR_UNSUPPORTED, "TF32X3 tensor-core path unavailable for this network: %s", why_not.c_str());
+        }
+    }
+    if (prec == ANNF_PREC_AUTO) {
+        if (h->macs <= (1 << 16) && h->tile_fp64 > 0) prec = ANNF_PREC_FP64;
+        else if (h->tensor != nullptr) prec = ANNF_PREC_TF32X3;
+        else prec = ANNF_PREC_FP32;
+    }
+    if (prec != ANNF_PREC_TF32X3 && h->tensor != nullptr) {
+        tensor_plan_destroy(h->tensor);
+        h->tensor = nullptr;
+    }
+    h->prec_batched = prec;
+    h->batched_path = prec == ANNF_PREC_TF32X3 ? 1 : 0;
+    if ((prec == ANNF_PREC_FP64 && h->tile_fp64 == 0) || (prec == ANNF_PREC_FP32 && h->tile_fp32 == 0)) {
+        release(h);
+        return fail(ANNF_ERR_UNSUPPORTED, "network too large for the fused batched kernel's shared memory in this precision");
+    }
+    ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    ANNF_CUDA_H(cudaDeviceSynchronize());
+#undef ANNF_CUDA_H
+    *out = h;
+    return ANNF_OK;
+}
+
+annf_status annf_destroy(annf_handle h) {
+    if (h == nullptr) return ANNF_OK;
+    release(h);
+    return ANNF_OK;
+}
+
+annf_status annf_get_info(annf_handle h, annf_info* info) {
+    if (!h || !info) return fail(ANNF_ERR_INVALID, "annf_get_info: NULL argument");
+    info->precision_single = h->prec_single;
+    info->precision_batched = h->prec_batched;
+    info->batched_path = h->batched_path;
+    info->cluster_size = h->cluster_size;
+    info->macs_per_eval = h->macs;
+    info->kernel_launches = h->launches;
+    info->sm_count = h->sm_count;
+    info->reserved = 0;
+    return ANNF_OK;
+}
+
+annf_status annf_update_parameters(annf_handle h, const double* potential_center, int32_t num_center,
+                                   double force_constant, void* stream) {
+    if (!h || !potential_center) return fail(ANNF_ERR_INVALID, "annf_update_parameters: NULL argument");
+    if (num_center != h->net.num_center)
+        return fail(ANNF_ERR_INVALID, "updateParametersInContext: potential_center has %d values, the context was built with %d",
+                    num_center, h->net.num_center);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    memcpy(h->staged_host, potential_center, sizeof(double) * num_center);
+    h->staged_host[num_center] = force_constant;
+    ANNF_CUDA(cudaMemcpyAsync(h->staged, h->staged_host, sizeof(double) * (num_center + 1), cudaMemcpyHostToDevice, s));
+    set_parameters_kernel<<<(num_center + 1 + 127) / 128, 128, 0, s>>>(h->center, h->staged, num_center, h->k_dev);
+    ANNF_CUDA(cudaGetLastError());
+    ANNF_CUDA(cudaStreamSynchronize(s));
+    h->launches++;
+    return ANNF_OK;
+}
+
+annf_status annf_set_atom_order(annf_handle h, const int32_t* atom_index_dev, int32_t num_atoms, void* stream) {
+    if (!h || !atom_index_dev) return fail(ANNF_ERR_INVALID, "annf_set_atom_order: NULL argument");
+    if (num_atoms != h->num_system_atoms)
+        return fail(ANNF_ERR_INVALID, "annf_set_atom_order: %d atoms, the handle was created for %d", num_atoms, h->num_system_atoms);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    invert_order_kernel<<<(num_atoms + 255) / 256, 256, 0, s>>>(atom_index_dev, num_atoms, h->inverse);
+    remap_kernel<<<(h->net.n_sel + 255) / 256, 256, 0, s>>>(h->sel_atoms, h->net.n_sel, h->inverse, h->sel_slots);
+    ANNF_CUDA(cudaGetLastError());
+    h->launches += 2;
+    return ANNF_OK;
+}
+
+annf_status annf_eval_openmm(annf_handle h, const void* posq, const void* posq_correction,
+                             unsigned long long* force_buffer, int32_t padded_num_atoms, void* energy_buffer,
+                             uint32_t flags, void* stream) {
+    if (!h || !posq) return fail(ANNF_ERR_INVALID, "annf_eval_openmm: NULL argument");
+    if (!force_buffer && !(flags & ANNF_FLAG_SKIP_FORCES)) return fail(ANNF_ERR_INVALID, "annf_eval_openmm: force_buffer is NULL");
+    if (padded_num_atoms < h->num_system_atoms)
+        return fail(ANNF_ERR_INVALID, "annf_eval_openmm: padded_num_atoms %d < %d atoms", padded_num_atoms, h->num_system_atoms);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    h->prof.begin("annf_single_kernel", s);
+    cudaError_t err = launch_single(h->net, h->cluster_size, posq, posq_correction, force_buffer, padded_num_atoms,
+                                    energy_buffer, flags, s);
+    h->prof.end(s);
+    if (err != cudaSuccess) return fail(ANNF_ERR_CUDA, "single-replica launch failed: %s", cudaGetErrorString(err));
+    h->launches++;
+    return ANNF_OK;
+}
+
+annf_status annf_eval_batched(annf_handle h, int32_t R, const float* coords, int32_t atoms_per_replica,
+                              const float* centers, float* forces, double* energies, void* stream) {
+    if (!h || !coords || !forces || !energies) return fail(ANNF_ERR_INVALID, "annf_eval_batched: NULL argument");
+    if (R < 0) return fail(ANNF_ERR_INVALID, "annf_eval_batched: num_replicas = %d", R);
+    if (atoms_per_replica < h->num_system_atoms)
+        return fail(ANNF_ERR_INVALID, "annf_eval_batched: atoms_per_replica %d < %d system atoms", atoms_per_replica, h->num_system_atoms);
+    if (R == 0) return ANNF_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    cudaError_t err;
+    if (h->batched_path == 1) {
+        err = tensor_plan_run(h->tensor, &h->prof, h->net, R, coords, atoms_per_replica, centers, forces, energies, s, &h->launches);
+    } else {
+        const bool fp64 = h->prec_batched == ANNF_PREC_FP64;
+        h->prof.begin(fp64 ? "annf_batched_kernel<f64>" : "annf_batched_kernel<f32>", s);
+        err = launch_batched(h->net, h->x_off, h->extra_nodes, fp64 ? h->tile_fp64 : h->tile_fp32, fp64, R, coords,
+                             atoms_per_replica, centers, forces, energies, s);
+        h->prof.end(s);
+        h->launches++;
+    }
+    if (err != cudaSuccess) return fail(ANNF_ERR_CUDA, "batched launch failed: %s", cudaGetErrorString(err));
+    return ANNF_OK;
+}
+
+annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords_host, int32_t atoms_per_replica,
+                                   const float* centers_host, float* forces_host, double* energies_host) {
+    if (!h || !coords_host || !forces_host || !energies_host) return fail(ANNF_ERR_INVALID, "annf_eval_batched_host: NULL argument");
+    if (R <= 0) return R == 0 ? ANNF_OK : fail(ANNF_ERR_INVALID, "annf_eval_batched_host: num_replicas = %d", R);
+    DeviceGuard guard(h->device);
+    const size_t n_coords = (size_t) R * atoms_per_replica * 3, n_centers = (size_t) R * h->net.num_center;
+    if (n_coords > h->h_cap_coords) {
+        cudaFree(h->h_coords); cudaFree(h->h_forces);
+        h->h_coords = h->h_forces = nullptr; h->h_cap_coords = 0;
+        ANNF_CUDA(cudaMalloc((void**) &h->h_coords, sizeof(float) * n_coords));
+        ANNF_CUDA(cudaMalloc((void**) &h->h_forces, sizeof(float) * n_coords));
+        h->h_cap_coords = n_coords;
+    }
+    if (centers_host && n_centers > h->h_cap_centers) {
+        cudaFree(h->h_centers); h->h_centers = nullptr; h->h_cap_centers = 0;
+        ANNF_CUDA(cudaMalloc((void**) &h->h_centers, sizeof(float) * n_centers));
+        h->h_cap_centers = n_centers;
+    }
+    if ((size_t) R > h->h_cap_energies) {
+        cudaFree(h->h_energies); h->h_energies = nullptr; h->h_cap_energies = 0;
+        ANNF_CUDA(cudaMalloc((void**) &h->h_energies, sizeof(double) * R));
+        h->h_cap_energies = R;
+    }
+    cudaStream_t s = h->host_stream;
+    ANNF_CUDA(cudaMemcpyAsync(h->h_coords, coords_host, sizeof(float) * n_coords, cudaMemcpyHostToDevice, s));
+    if (centers_host)
+        ANNF_CUDA(cudaMemcpyAsync(h->h_centers, centers_host, sizeof(float) * n_centers, cudaMemcpyHostToDevice, s));
+    // the kernels write the selected atoms only; everything else in forces_host comes back as zero
+    if (h->net.n_sel != atoms_per_replica) ANNF_CUDA(cudaMemsetAsync(h->h_forces, 0, sizeof(float) * n_coords, s));
+    annf_status st = annf_eval_batched(h, R, h->h_coords, atoms_per_replica, centers_host ? h->h_centers : nullptr,
+                                       h->h_forces, h->h_energies, s);
+    if (st != ANNF_OK) return st;
+    ANNF_CUDA(cudaMemcpyAsync(forces_host, h->h_forces, sizeof(float) * n_coords, cudaMemcpyDeviceToHost, s));
+    ANNF_CUDA(cudaMemcpyAsync(energies_host, h->h_energies, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
+    ANNF_CUDA(cudaStreamSynchronize(s));
+    return ANNF_OK;
+}
+
+annf_status annf_set_profiling(annf_handle h, int32_t enabled) {
+    if (!h) return fail(ANNF_ERR_INVALID, "annf_set_profiling: NULL handle");
+    DeviceGuard guard(h->device);
+    if (!enabled) h->prof.drain();
+    h->prof.enabled = enabled != 0;
+    return ANNF_OK;
+}
+
+annf_status annf_get_kernel_times(annf_handle h, annf_kernel_time* out, int32_t capacity, int32_t* count, int32_t reset) {
+    if (!h || !count) return fail(ANNF_ERR_INVALID, "annf_get_kernel_times: NULL argument");
+    DeviceGuard guard(h->device);
+    h->prof.drain();
+    int n = 0;
+    for (auto& kv : h->prof.totals) {
+        if (out && n < capacity) {
+            memset(&out[n], 0, sizeof(annf_kernel_time));
+            strncpy(out[n].name, h->prof.names[kv.first].c_str(), sizeof(out[n].name) - 1);
+            out[n].launches = kv.second.first;
+            out[n].total_ms = kv.second.second;
+        }
+        n++;
+    }
+    *count = n;
+    if (reset) h->prof.totals.clear();
+    return ANNF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Shared host/device definitions of libannforce_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "annforce_b200.h"
+
+namespace annf {
+
+constexpr int kMaxLayers = ANNF_MAX_LAYERS;
+constexpr double kTwoPiRef = 6.2832;   // the reference's 2*pi (ANN_ReferenceKernels.h:106-107, .cpp:282-283)
+
+// Device view of one network.  All pointers are device pointers owned by the handle.
+struct NetView {
+    int L;                          // node layers
+    int nodes[kMaxLayers];
+    int types[kMaxLayers];          // types[l] = activation producing layer l+1
+    int node_off[kMaxLayers + 1];   // prefix sums of nodes (activation offsets)
+    long long w_off[kMaxLayers];    // offset of connection l in the flat weight arrays
+    int b_off[kMaxLayers];          // offset of connection l in the flat bias arrays
+    const double* W64;              // [n_out][n_in] per connection   (backward: lanes over n_in)
+    const double* Wt64;             // [n_in][n_out] per connection   (forward:  lanes over n_out)
+    const float* W32;
+    const float* Wt32;
+    const double* b64;
+    const float* b32;
+    const double* center;           // [num_center] device copy (annf_update_parameters rewrites it)
+    const double* k_dev;            // force constant on the device (same reason)
+    int num_center;
+    double scale;                   // scaling_factor
+    int input_type;
+    int n_sel;                      // selected atoms (Cartesian)
+    const int* sel_atoms;           // 0-based original atom index per selected atom
+    const int* sel_slots;           // position-buffer slot per selected atom (OpenMM reordering)
+    int n_pairs;
+    const int* pairs;               // 0-based original atom indices, [2*n_pairs]
+    const int* pair_slots;
+    int n_dihedrals;
+    const int* dihedrals;           // [4*n_dihedrals]
+    const int* dihedral_slots;
+};
+
+template <typename T> struct WeightsOf;
+template <> struct WeightsOf<double> {
+    __device__ static const double* W(const NetView& n) { return n.W64; }
+    __device__ static const double* Wt(const NetView& n) { return n.Wt64; }
+    __device__ static const double* b(const NetView& n) { return n.b64; }
+};
+template <> struct WeightsOf<float> {
+    __device__ static const float* W(const NetView& n) { return n.W32; }
+    __device__ static const float* Wt(const NetView& n) { return n.Wt32; }
+    __device__ static const float* b(const NetView& n) { return n.b32; }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double act_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float act_tanh(float x) { return tanhf(x); }
+
+// ---------------------------------------------------------------------------------------------
+// Output head in fp64, one replica, executed by ONE thread (n_last is a handful of CVs).
+//   in : z[n]   pre-activations of the output layer (stride zs)
+//   out: dz[n]  dE/dz of the output layer (stride ds); returns the umbrella energy.
+// Follows update_and_get_potential_energy (ANN_ReferenceKernels.h:89-119) and the output-layer part
+// of back_prop (ANN_ReferenceKernels.cpp:265-296) composed with that layer's own Jacobian
+// (:307-318 Circular, :343-348 Tanh, :349-354 Linear, :355-365 Softmax).
+// ---------------------------------------------------------------------------------------------
+__device__ inline double output_head(int type, int n, const double* z, int zs, const double* center, double k,
+                                     double* dz, int ds) {
+    double e = 0.0;
+    if (type == ANNF_CIRCULAR) {
+        for (int j = 0; j < n / 2; j++) {
+            const double p = z[(2 * j) * zs], q = z[(2 * j + 1) * zs];
+            const double r = sqrt(p * p + q * q);
+            const double c = p / r, s = q / r;                       // :213-216
+            const int sign = s > 0 ? 1 : -1;                         // :279, .h:102
+            const double angle = acos(c) * sign;
+            const double d1 = angle - center[j], d2 = d1 + kTwoPiRef, d3 = d1 - kTwoPiRef;
+            double dist = d1;                                         // :285-291
+            if (fabs(d2) < fabs(dist)) dist = d2;
+            if (fabs(d3) < fabs(dist)) dist = d3;
+            e += 0.5 * k * fmin(fmin(d1 * d1, d2 * d2), d3 * d3);     // .h:109-114
+            const double d_cos = k * dist * (-1) / sqrt(1 - c * c) * sign;   // :292-293 ; d_sin = 0 (:294)
+            // Circular Jacobian (:309-317) applied to (d_cos, 0)
+            dz[(2 * j) * ds] = q / (r * r * r) * (q * d_cos);
+            dz[(2 * j + 1) * ds] = p / (r * r * r) * (-q * d_cos);
+        }
+    } else if (type == ANNF_SOFTMAX) {
+        double sum = 0.0;                                             // no max-shift, like :226-234
+        for (int j = 0; j < n; j++) sum += exp(z[j * zs]);
+        double dot = 0.0;
+        for (int j = 0; j < n; j++) {
+            const double a = exp(z[j * zs]) / sum, d = (a - center[j]) * k;
+            e += 0.5 * k * (a - center[j]) * (a - center[j]);
+            dot += a * d;
+        }
+        for (int j = 0; j < n; j++) {                                 // sum_s (delta_js - a_j) a_s d_s  (:355-365)
+            const double a = exp(z[j * zs]) / sum, d = (a - center[j]) * k;
+            dz[j * ds] = a * d - a * dot;
+        }
+    } else {
+        for (int j = 0; j < n; j++) {
+            const double zz = z[j * zs];
+            const double a = (type == ANNF_TANH) ? tanh(zz) : zz;
+            const double d = (a - center[j]) * k;                      // :266-269
+            e += 0.5 * k * (a - center[j]) * (a - center[j]);          // .h:93-96
+            dz[j * ds] = (type == ANNF_TANH) ? d * (1 - a * a) : d;    // :343-354
+        }
+    }
+    return e;
+}
+
+}  // namespace annf

@@ -1,0 +1,301 @@
+// Single-replica fused kernel on OpenMM's device buffers (sm_100a).
+//
+// One launch = one ANN_Force evaluation: gather posq -> scale / remove centroid -> MLP forward ->
+// umbrella energy -> analytic backward -> centring Jacobian -> atomicAdd into the fixed-point force
+// buffer.  It replaces the 60-"bond" generated snippet the legacy plugin handed to
+// CudaBondedUtilities (/root/reference/platforms/cuda/src/CudaANN_Kernels.cpp:180-359) and follows
+// the arithmetic of ReferenceCalcANN_ForceKernel::candidate_2
+// (/root/reference/platforms/reference/ANN_ReferenceKernels.cpp:122-171) in fp64.
+//
+// Parallel decomposition: ONE thread-block cluster of `CL` CTAs (1 for small nets, up to 16 for wide
+// layers).  Every CTA keeps the full activation vectors in its own shared memory; each computes a
+// contiguous slice of a layer's rows (forward) or columns (backward) and publishes the slice into
+// every peer's shared memory through DSMEM stores, followed by one cluster barrier.  Within a CTA a
+// forward row is a warp-wide dot product reduced with shuffles; a backward column is one thread
+// walking the (coalesced) weight rows.  Weights are read straight from L2/L1 (they are touched
+// exactly once per direction per evaluation, so staging them in shared memory would not save a byte).
+#include <cooperative_groups.h>
+
+#include "annf_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace annf {
+
+constexpr int kSingleThreads = 256;
+constexpr int kSingleWarps = kSingleThreads / 32;
+
+struct SingleArgs {
+    NetView net;
+    const void* posq;
+    const void* posq_corr;
+    unsigned long long* force;
+    int padded;
+    void* energy;
+    unsigned flags;
+};
+
+// Position of one atom slot in nm, fp64, honouring single / mixed (+correction) / double layouts.
+__device__ __forceinline__ double3 load_pos(const SingleArgs& a, int slot) {
+    if (a.flags & ANNF_FLAG_POSQ_DOUBLE) {
+        const double4 p = reinterpret_cast<const double4*>(a.posq)[slot];
+        return make_double3(p.x, p.y, p.z);
+    }
+    const float4 p = __ldg(reinterpret_cast<const float4*>(a.posq) + slot);
+    double3 r = make_double3((double) p.x, (double) p.y, (double) p.z);
+    if (a.posq_corr != nullptr) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(a.posq_corr) + slot);
+        r.x += (double) c.x; r.y += (double) c.y; r.z += (double) c.z;
+    }
+    return r;
+}
+
+// Write v into the same shared-memory location of every CTA of the cluster.
+__device__ __forceinline__ void publish(cg::cluster_group& cluster, int cl, double* local_ptr, double v, int lane) {
+    if (cl == 1) {
+        if (lane == 0) *local_ptr = v;
+    } else if (lane < cl) {
+        *cluster.map_shared_rank(local_ptr, lane) = v;
+    }
+}
+
+__device__ __forceinline__ void cluster_or_block_sync(cg::cluster_group& cluster, int cl) {
+    if (cl == 1) __syncthreads();
+    else cluster.sync();
+}
+
+// In-place activation of a full layer held in shared memory (every CTA does this redundantly).
+//   z -> a ; types per ANN_ReferenceKernels.cpp:200-234
+__device__ void activate_layer(int type, int n, const double* z, double* a) {
+    const int tid = threadIdx.x;
+    if (type == ANNF_LINEAR) {
+        for (int j = tid; j < n; j += blockDim.x) a[j] = z[j];
+    } else if (type == ANNF_TANH) {
+        for (int j = tid; j < n; j += blockDim.x) a[j] = tanh(z[j]);
+    } else if (type == ANNF_CIRCULAR) {
+        for (int j = tid; j < n / 2; j += blockDim.x) {
+            const double p = z[2 * j], q = z[2 * j + 1], r = sqrt(p * p + q * q);
+            a[2 * j] = p / r;
+            a[2 * j + 1] = q / r;
+        }
+    } else {
+        for (int j = tid; j < n; j += blockDim.x) {
+            double sum = 0.0;
+            for (int s = 0; s < n; s++) sum += exp(z[s]);
+            a[j] = exp(z[j]) / sum;
+        }
+    }
+}
+
+// dE/da -> dE/dz of a hidden layer, full vector in shared memory, in place in d[].
+// (ANN_ReferenceKernels.cpp:307-318 Circular, :343-348 Tanh, :349-354 Linear, :355-365 Softmax)
+__device__ void activation_backward(int type, int n, const double* z, const double* a, double* d, double* scratch) {
+    const int tid = threadIdx.x;
+    if (type == ANNF_TANH) {
+        for (int j = tid; j < n; j += blockDim.x) d[j] *= (1 - a[j] * a[j]);
+    } else if (type == ANNF_CIRCULAR) {
+        for (int j = tid; j < n / 2; j += blockDim.x) {
+            const double p = z[2 * j], q = z[2 * j + 1], r = sqrt(p * p + q * q);
+            const double dp = d[2 * j], dq = d[2 * j + 1];
+            d[2 * j] = q / (r * r * r) * (q * dp - p * dq);
+            d[2 * j + 1] = p / (r * r * r) * (p * dq - q * dp);
+        }
+    } else if (type == ANNF_SOFTMAX) {
+        for (int j = tid; j < n; j += blockDim.x) {
+            double dot = 0.0;
+            for (int s = 0; s < n; s++) dot += a[s] * d[s];
+            scratch[j] = a[j] * d[j] - a[j] * dot;
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += blockDim.x) d[j] = scratch[j];
+    }
+}
+
+__global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const SingleArgs args) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cl = (int) cluster.num_blocks();
+    const int rank = (int) cluster.block_rank();
+    const NetView& net = args.net;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = net.L, total = net.node_off[L];
+
+    extern __shared__ double smem[];
+    double* a = smem;                 // activations  a[node_off[l] + j]
+    double* z = a + total;            // pre-activations
+    double* d = z + total;            // dE/dz (hidden/output layers), dE/dx (layer 0)
+    double* red = d + total;          // [8] small reductions / broadcasts
+    __shared__ double s_energy;
+
+    // every CTA of the cluster must be resident before anyone stores into a peer's shared memory
+    if (cl > 1) cluster.sync();
+
+    // ---- feature stage: ANN_ReferenceKernels.cpp:128-151 (Cartesian) -------------------------
+    // every CTA builds the full, centred input redundantly (it is 3*A values)
+    const int n0 = net.nodes[0];
+    if (net.input_type == ANNF_INPUT_CARTESIAN) {
+        const int A = net.n_sel;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int i = tid; i < A; i += kSingleThreads) {
+            const double3 p = load_pos(args, net.sel_slots[i]);
+            const double x = p.x / net.scale, y = p.y / net.scale, w = p.z / net.scale;   // :139
+            a[3 * i] = x; a[3 * i + 1] = y; a[3 * i + 2] = w;
+            sx += x; sy += y; sz += w;
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        if (lane == 0) { red[8 + 3 * warp] = sx; red[8 + 3 * warp + 1] = sy; red[8 + 3 * warp + 2] = sz; }
+        __syncthreads();
+        if (tid < 3) {
+            double s = 0.0;
+            for (int w = 0; w < kSingleWarps; w++) s += red[8 + 3 * w + tid];
+            red[tid] = s / A;                                                             // unweighted centroid :137-141
+        }
+        __syncthreads();
+        for (int i = tid; i < n0; i += kSingleThreads) a[i] -= red[i % 3];                // :143-145
+    }
+    __syncthreads();
+
+    // ---- forward: calculate_output_of_each_layer, ANN_ReferenceKernels.cpp:179-260 -------------
+    for (int l = 0; l + 1 < L; l++) {
+        const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+        const double* W = net.W64 + net.w_off[l];
+        const double* b = net.b64 + net.b_off[l];
+        const double* ain = a + net.node_off[l];
+        double* zout = z + net.node_off[l + 1];
+        const int per = (n_out + cl - 1) / cl;
+        const int j0 = rank * per, j1 = min(n_out, j0 + per);
+        // a warp owns rows j0+warp, +8, +16, +24 (four independent dot products in flight), then +32 ...
+        for (int jb = j0 + warp; jb < j1; jb += 4 * kSingleWarps) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = lane; i < n_in; i += 32) {
+                const double x = ain[i];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = jb + u * kSingleWarps;
+                    if (j < j1) acc[u] = fma(__ldg(W + (size_t) j * n_in + i), x, acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = jb + u * kSingleWarps;
+                const double s = warp_sum(acc[u]);
+                if (j < j1) publish(cluster, cl, zout + j, s + b[j], lane);                // :193-198
+            }
+        }
+        cluster_or_block_sync(cluster, cl);
+        if (l + 2 < L) {   // hidden layer: activate the whole vector locally
+            activate_layer(net.types[l], n_out, zout, a + net.node_off[l + 1]);
+            __syncthreads();
+        }
+    }
+
+    // ---- energy + output-layer gradient (fp64, one thread per CTA, identical in every CTA) -----
+    if (tid == 0) {
+        const int n_last = net.nodes[L - 1];
+        s_energy = output_head(net.types[L - 2], n_last, z + net.node_off[L - 1], 1, net.center, *net.k_dev,
+                               d + net.node_off[L - 1], 1);
+    }
+    __syncthreads();
+
+    // ---- backward: back_prop, ANN_ReferenceKernels.cpp:299-373 ----------------------------------
+    for (int l = L - 2; l >= 0; l--) {
+        const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+        const double* W = net.W64 + net.w_off[l];
+        const double* dz = d + net.node_off[l + 1];
+        double* dout = d + net.node_off[l];
+        const int per = (n_in + cl - 1) / cl;
+        const int m0 = rank * per, m1 = min(n_in, m0 + per);
+        for (int m = m0 + tid; m < m1; m += kSingleThreads) {
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            int k = 0;
+            for (; k + 4 <= n_out; k += 4) {
+                acc0 = fma(__ldg(W + (size_t) (k + 0) * n_in + m), dz[k + 0], acc0);
+                acc1 = fma(__ldg(W + (size_t) (k + 1) * n_in + m), dz[k + 1], acc1);
+                acc2 = fma(__ldg(W + (size_t) (k + 2) * n_in + m), dz[k + 2], acc2);
+                acc3 = fma(__ldg(W + (size_t) (k + 3) * n_in + m), dz[k + 3], acc3);
+            }
+            for (; k < n_out; k++) acc0 = fma(__ldg(W + (size_t) k * n_in + m), dz[k], acc0);
+            const double v = (acc0 + acc1) + (acc2 + acc3);
+            if (cl == 1) {
+                dout[m] = v;
+            } else {
+                for (int r = 0; r < cl; r++) *cluster.map_shared_rank(dout + m, r) = v;
+            }
+        }
+        cluster_or_block_sync(cluster, cl);
+        if (l >= 1) {
+            activation_backward(net.types[l - 1], n_in, z + net.node_off[l], a + net.node_off[l], dout, red + 8);
+            __syncthreads();
+        }
+    }
+
+    // ---- forces: get_all_forces_from_derivative_of_first_layer, ANN_ReferenceKernels.cpp:397-410 --
+    if (!(args.flags & ANNF_FLAG_SKIP_FORCES) && net.input_type == ANNF_INPUT_CARTESIAN) {
+        const int A = net.n_sel;
+        const double* g = d;   // dE/dx, layer 0
+        // mean gradient per component = the Jacobian term of centroid removal (:402-406), O(A) not O(A^2)
+        if (warp < 3) {
+            double s = 0.0;
+            for (int i = lane; i < A; i += 32) s += g[3 * i + warp];
+            s = warp_sum(s);
+            if (lane == 0) red[warp] = s / A;
+        }
+        __syncthreads();
+        const int per = (A + cl - 1) / cl;
+        const int i0 = rank * per, i1 = min(A, i0 + per);
+        for (int t = 3 * i0 + tid; t < 3 * i1; t += kSingleThreads) {
+            const int i = t / 3, c = t - 3 * i;
+            const double f = -(g[t] - red[c]) / net.scale;
+            atomicAdd(&args.force[net.sel_slots[i] + c * args.padded],
+                      (unsigned long long) ((long long) (f * (double) 0x100000000LL)));
+        }
+    }
+    if (rank == 0 && tid == 0 && args.energy != nullptr && !(args.flags & ANNF_FLAG_SKIP_ENERGY)) {
+        if (args.flags & ANNF_FLAG_ENERGY_DOUBLE) reinterpret_cast<double*>(args.energy)[0] += s_energy;
+        else reinterpret_cast<float*>(args.energy)[0] += (float) s_energy;
+    }
+}
+
+size_t single_smem_bytes(const NetView& net) {
+    const int total = net.node_off[net.L];
+    int max_n = 0;
+    for (int l = 0; l < net.L; l++) max_n = net.nodes[l] > max_n ? net.nodes[l] : max_n;
+    return sizeof(double) * (3 * (size_t) total + 8 + (size_t) (max_n > 3 * kSingleWarps ? max_n : 3 * kSingleWarps));
+}
+
+cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq, const void* posq_corr,
+                          unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream) {
+    SingleArgs args;
+    args.net = net;
+    args.posq = posq;
+    args.posq_corr = posq_corr;
+    args.force = force;
+    args.padded = padded;
+    args.energy = energy;
+    args.flags = flags;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(kSingleThreads);
+    cfg.dynamicSmemBytes = single_smem_bytes(net);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, annf_single_kernel, args);
+}
+
+cudaError_t prepare_single(const NetView& net, int cluster_size) {
+    // function attributes are per device, not per handle: always ask for the architectural maximum so
+    // that handles of different sizes can coexist
+    (void) net;
+    cudaError_t err = cudaFuncSetAttribute(annf_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) return err;
+    if (cluster_size > 8)
+        err = cudaFuncSetAttribute(annf_single_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return err;
+}
+
+}  // namespace annf

@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Headline benchmark of the ANN bias-force hot path (contract in the task statement, §④).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic replicas: every replica's
+coordinates -> MLP forward -> umbrella energy -> analytic backward -> forces.  The default workload
+is BASELINE.json configs[4] sharded the way it is quoted: 4500-512-512-8 encoder on 1500 atoms,
+1024 replicas PER GPU (8192 on 8 GPUs) — weak scaling, no collective on the force path.  Other
+BASELINE shapes are selectable with --workload (c2 single replica on OpenMM buffers, c3, c4).
+
+Prints ONE JSON line (rank 0).  `value` is whole-job evaluations/s with inputs resident in HBM;
+`e2e` is the same metric through the host-buffer C-ABI entry (H2D + eval + D2H every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ann_force_b200 import synthetic  # noqa: E402
+
+METRIC = "ANN bias force evals/sec (replicas x steps)"
+UNIT = "evals/s"
+L2_BYTES = 126 * 1024 * 1024
+TIMESTEP_FS = 2.0          # ns/day = steps/s per replica * dt * 86400 s/day
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is None:
+            return
+        try:
+            self.samples.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+            mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            self._stop.wait(0.01)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=0)
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(self.samples))
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU implementation (oracle/_ref), or the C restatement when it is absent
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(workload, force, atoms, target_core_seconds, steps=1, warmup=0):
+    """Times the reference CPU kernel on a bounded sample of the workload, all host cores busy
+    (the reference is single-threaded; replicas are independent, so they are spread over threads).
+    Returns (evals_per_s, info)."""
+    from oracle import port
+    from oracle import reference as ref
+    depth = len(force.get_num_of_nodes())
+    cores = host_cores()
+    use_ref = ref.available(depth)
+    kind = "reference" if use_ref else "port"
+    threads = cores if use_ref else 1
+
+    def run(n):
+        pos = synthetic.make_positions(atoms, n, seed=99).astype(np.float64)
+        cen = synthetic.make_centers(force, n, seed=98).astype(np.float64)
+        if use_ref:
+            _, _, secs = ref.evaluate(force, pos, cen, threads=threads, return_seconds=True)
+        else:
+            _, _, secs = port.evaluate(force, pos, cen, return_seconds=True)
+        return secs
+
+    probe_n = threads
+    probe = run(probe_n)                                   # one evaluation per thread
+    per_eval_core_s = probe * threads / probe_n
+    n = int(max(threads, min(200000, target_core_seconds / max(per_eval_core_s, 1e-9))))
+    n = (n // threads) * threads
+    for _ in range(warmup):
+        run(n)
+    secs = [run(n) for _ in range(max(1, steps))]
+    mean = float(np.mean(secs))
+    info = dict(kind=kind, cores=threads, value=n / mean, unit=UNIT,
+                sample="%d replicas of %s per step, %d step(s), %.2f s/step wall on %d thread(s); %s" % (
+                    n, workload, max(1, steps), mean, threads,
+                    "oracle/_ref = reference ANN_ReferenceKernels.cpp unmodified, g++ -O2" if use_ref
+                    else "oracle/ann_oracle.c restatement, gcc -O2"))
+    return n / mean, mean, n, info
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="c5", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU (default: the workload's)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp64", "fp32", "tf32x3"])
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = synthetic.CONFIGS[args.workload]
+    R = args.replicas or cfg["replicas"]
+    atoms = cfg["atoms"]
+    force = synthetic.make_config(args.workload)
+    nodes = cfg["nodes"]
+    flops_eval = synthetic.flops_per_eval(nodes)
+    config = dict(workload="%s: %s" % (args.workload, cfg["label"]), layer_sizes="-".join(map(str, nodes)),
+                  layer_types=cfg["types"], selected_atoms=atoms, replicas_per_gpu=R, replicas_total=R * world,
+                  parallelism="replicas sharded, %d per GPU, no collective on the force path" % R,
+                  flops_per_eval=flops_eval, bytes_per_eval=synthetic.bytes_per_eval(atoms, len(force.get_potential_center())))
+
+    # ---------------- reference arm: the reference's CPU implementation on the host cores -------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = args.steps if args.steps is not None else 3
+        warmup = args.warmup if args.warmup is not None else 1
+        # bounded sample per step: ~3 s of wall time on all cores, so K + W steps stay within minutes
+        steps_eff, warm_eff = min(steps, 20), min(warmup, 3)
+        value, sec_per_step, n, info = cpu_reference(args.workload, force, atoms, 3.0 * host_cores(), steps_eff, warm_eff)
+        line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=steps, warmup=warmup,
+                    ms_per_step=1e3 * sec_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", config=dict(config, sample_replicas_per_step=n, steps_run=steps_eff, warmup_run=warm_eff),
+                    cpu_baseline=info, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, ns_per_day_per_replica=(value / n) * TIMESTEP_FS * 1e-6 * 86400.0)
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm ---------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+
+    from ann_force_b200.kernel import CalcANNForce
+    from ann_force_b200.openmm_buffers import CudaContextBuffers
+    from ann_force_b200.replica import ReplicaSharder
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    peaks = load_peaks()
+
+    kernel = CalcANNForce(precision=args.precision)
+    kernel.initialize(atoms, force)
+    info = kernel.info()
+    single = (R == 1)
+
+    # per-rank synthetic inputs (different seeds per rank: every GPU has its own replicas)
+    per_step_bytes = R * atoms * 3 * 4 * 2 + R * 8
+    nbuf = 1 if single else int(min(64, max(2, (2 * L2_BYTES) // max(per_step_bytes, 1) + 1)))
+    rotate = nbuf * per_step_bytes > L2_BYTES
+    flush = None
+    if not rotate:
+        flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    centers_np = synthetic.make_centers(force, R, seed=777 + rank)
+    if single:
+        ctx = CudaContextBuffers(atoms, "mixed", device=dev)
+        ctx.set_positions(synthetic.make_positions(atoms, 1, seed=4321 + rank)[0])
+    else:
+        coords = [torch.as_tensor(synthetic.make_positions(atoms, R, seed=4321 + 17 * rank + b), device=dev) for b in range(nbuf)]
+        forces = [torch.empty_like(coords[0]) for _ in range(nbuf)]
+        energies = [torch.empty(R, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+        centers = torch.as_tensor(centers_np, device=dev)
+
+    def step(i):
+        if single:
+            kernel.execute(ctx, True, True)
+        else:
+            b = i % nbuf
+            kernel.execute_batched(coords[b], centers, forces[b], energies[b])
+
+    steps = args.steps if args.steps is not None else (2000 if args.workload == "c5" else 5000)
+    warmup = args.warmup if args.warmup is not None else 20
+    warmup = max(warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = kernel.info()["kernel_launches"]
+    kernel.set_profiling(True)
+    kernel.kernel_times(reset=True)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    if rotate or single:
+        barrier()
+        t0 = time.perf_counter()
+        start.record()
+        for i in range(steps):
+            step(i)
+            if i == steps // 2:
+                sampler.sample()
+        stop.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        gpu_ms = start.elapsed_time(stop)
+        l2_policy = ("single replica: inputs are one 7-atom frame, L2-resident by nature" if single else
+                     "rotating %d input/output buffer sets (%.0f MB) > 126 MB L2" % (nbuf, nbuf * per_step_bytes / 1e6))
+    else:
+        # small batches: flush L2 between steps and time each step with its own event pair
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            evs[i][0].record()
+            step(i)
+            evs[i][1].record()
+            if i == steps // 2:
+                sampler.sample()
+        barrier()
+        wall = time.perf_counter() - t0
+        gpu_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+        l2_policy = "L2 flushed (252 MB write) between steps; each step timed with its own CUDA event pair"
+    sampler.stop()
+    kernel.set_profiling(False)
+    times = kernel.kernel_times(reset=True)
+    launches = kernel.info()["kernel_launches"] - launches0
+
+    t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gpu_ms_max = float(t.item())
+    total_evals = R * world * steps
+    value = total_evals / (gpu_ms_max * 1e-3)
+
+    # ---------------- end to end through the host-buffer C-ABI entry ----------------------------------------------
+    e2e = None
+    if not single:
+        e2e_steps = args.e2e_steps or max(10, min(steps, 200))
+        h_coords = [torch.as_tensor(synthetic.make_positions(atoms, R, seed=9000 + 17 * rank + b)).pin_memory() for b in range(2)]
+        h_centers = torch.as_tensor(centers_np).pin_memory()
+        h_forces = torch.empty_like(h_coords[0]).pin_memory()
+        h_energies = torch.empty(R, dtype=torch.float64).pin_memory()
+        for i in range(3):
+            kernel.execute_batched_host(h_coords[i % 2], h_centers, h_forces, h_energies)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            kernel.execute_batched_host(h_coords[i % 2], h_centers, h_forces, h_energies)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = dict(value=R * world * e2e_steps / float(tt.item()), unit=UNIT,
+                   h2d_bytes_per_step=int(h_coords[0].numel() * 4 + h_centers.numel() * 4),
+                   d2h_bytes_per_step=int(h_forces.numel() * 4 + h_energies.numel() * 8),
+                   steps=e2e_steps, ms_per_step=1e3 * float(tt.item()) / e2e_steps,
+                   api="CalcANNForce.execute_batched_host -> annf_eval_batched_host (pinned host buffers)")
+    else:
+        # single replica: the public call IS the OpenMM-buffer entry; positions already live on the device in OpenMM.
+        e2e = dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                   note="OpenMM keeps positions/forces on the device; the per-step call has no host traffic")
+
+    # optional replica-exchange all-gather of energies (outside the timed force path)
+    exchange_us = None
+    if world > 1 and not single:
+        sharder = ReplicaSharder(R * world)
+        torch.cuda.synchronize()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        sharder.gather_energies(energies[0])
+        g0.record()
+        for _ in range(10):
+            sharder.gather_energies(energies[0])
+        g1.record()
+        torch.cuda.synchronize()
+        exchange_us = 1e3 * g0.elapsed_time(g1) / 10
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel --------------------------------------------------------------
+    dominant = max(times.items(), key=lambda kv: kv[1]["total_ms"]) if times else (None, None)
+    roofline = None
+    if dominant[0] is not None:
+        name, rec = dominant
+        avg_ms = rec["total_ms"] / max(rec["launches"], 1)
+        kflops = kernel_flops(name, nodes, R, flops_eval)
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        achieved = kflops / (avg_ms * 1e-3) / 1e12
+        roofline = dict(bound="tensor", kernel=name, achieved=achieved, peak=tf32_peak, unit="TFLOP/s",
+                        frac=achieved / tf32_peak, traffic=load_traffic(name),
+                        avg_launch_ms=avg_ms, launches=rec["launches"],
+                        share_of_step=rec["total_ms"] / max(sum(v["total_ms"] for v in times.values()), 1e-12),
+                        algorithmic_flops_per_launch=kflops,
+                        peak_source="%s bf16_tflops_sustained / 2 (dense TF32 = half the bf16 rate; a 3xTF32 kernel tops out at frac 1/3)"
+                                    % peaks["source"],
+                        kernels={k: dict(launches=v["launches"], avg_ms=v["total_ms"] / max(v["launches"], 1)) for k, v in times.items()})
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        _, _, _, cpu = cpu_reference(args.workload, force, atoms, 15.0)
+
+    steps_per_s_per_replica = steps / (gpu_ms_max * 1e-3)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
+                ms_per_step=gpu_ms_max / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype={"fp64": "f64", "fp32": "f32", "tf32x3": "tf32x3 (fp32 accumulate)"}[info["precision_single" if single else "precision_batched"]],
+                data="synthetic", config=dict(config, l2=l2_policy, path=info["batched_path"] if not single else "single-replica cluster kernel",
+                                              wall_ms_per_step=1e3 * wall / steps),
+                clocks=sampler.summary(), e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                ns_per_day_per_replica=steps_per_s_per_replica * TIMESTEP_FS * 1e-6 * 86400.0,
+                exchange_allgather_us=exchange_us)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_flops(name, nodes, R, flops_eval):
+    """Algorithmic flops of one launch of the named kernel."""
+    if name.startswith("gemm["):
+        # tensor path names its GEMMs gemm[MxNxK]...
+        m, n, k = (int(v) for v in name[5:name.index("]")].split("x"))
+        return 2.0 * m * n * k
+    return float(flops_eval) * R          # fused kernels do the whole evaluation
+
+
+def load_traffic(name):
+    """dram bytes per launch from the committed ncu capture of this kernel, if there is one."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(name)
+    return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

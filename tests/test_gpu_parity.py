@@ -1,0 +1,267 @@
+"""Parity of the CUDA path with the oracle, through the public kernel object / C-ABI (run with -m gpu).
+
+Bars (BASELINE.json north_star): energy within 1e-6 relative, forces within 1e-4 relative max-norm.
+The fp64 paths are held to far tighter numbers, written at each assert.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import golden_io
+from ann_force_b200 import ANN_Force, _capi, synthetic
+from ann_force_b200.kernel import CalcANNForce
+from ann_force_b200.openmm_buffers import CudaContextBuffers
+from gpu_utils import max_norm_rel, run_batched, run_single
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-6      # north_star energy bar
+F_RTOL = 1e-4      # north_star force bar (relative max-norm)
+FIXED_POINT_ULP = 2.0 ** -32   # OpenMM's force buffer resolution, kJ/mol/nm
+
+CARTESIAN_GOLDEN = [n for n in golden_io.names()
+                    if golden_io.load(n)[5]["data_type_in_input_layer"] == 1]
+
+
+def test_library_reports_device():
+    assert _capi.lib().annf_device_count() >= 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# single replica on OpenMM-layout buffers
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CARTESIAN_GOLDEN)
+@pytest.mark.parametrize("precision", ["single", "mixed", "double"])
+def test_single_replica_matches_golden(name, precision):
+    force, pos, centers, energies, forces, _ = golden_io.load(name)
+    for r in range(min(pos.shape[0], 3)):
+        f = force
+        if centers is not None:
+            f, _, _, _, _, _ = golden_io.load(name)
+            f.set_potential_center(centers[r])
+        e, frc, seen, _ = run_single(f, pos[r], precision)
+        if precision == "single":
+            # the device holds fp32 positions: compare with the oracle on exactly those
+            e_ref, f_ref = port.evaluate(f, seen)
+        else:
+            np.testing.assert_allclose(seen, pos[r], rtol=0, atol=1e-12)
+            e_ref, f_ref = (energies[r], forces[r]) if centers is None else port.evaluate(f, pos[r])
+        tol_e = 1e-6 if precision == "single" else 1e-11   # single: fp32 energy buffer
+        assert abs(e - e_ref) <= tol_e * abs(e_ref), (name, r, e, e_ref)
+        assert np.abs(frc - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+
+
+def test_single_replica_reordered_atoms_and_accumulation():
+    force, pos, _, _, _, _ = golden_io.load("syn_shuffled_atoms")
+    n = pos.shape[1]
+    order = np.random.default_rng(3).permutation(n)
+    e1, f1, seen, _ = run_single(force, pos[0], "double", order=order)
+    e_ref, f_ref = port.evaluate(force, pos[0])
+    assert abs(e1 - e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(f1 - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+    # forces and energy ACCUMULATE into the context buffers (ANN_ReferenceKernels.cpp:401 `+=`)
+    e2, f2, _, _ = run_single(force, pos[0], "double", order=order, repeats=2)
+    assert abs(e2 - 2 * e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(f2 - 2 * f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 4 * FIXED_POINT_ULP
+    # atoms outside the selection are untouched
+    sel = np.asarray(force.get_index_of_backbone_atoms()) - 1
+    mask = np.ones(n, dtype=bool); mask[sel] = False
+    assert np.all(f1[mask] == 0.0)
+
+
+@pytest.mark.parametrize("config", ["c1", "c2", "c4"])
+def test_single_replica_baseline_shapes(config):
+    cfg = synthetic.CONFIGS[config]
+    force = synthetic.make_config(config)
+    pos = synthetic.make_positions(cfg["atoms"], 1)[0]
+    e, frc, seen, kernel = run_single(force, pos, "mixed")
+    e_ref, f_ref = port.evaluate(force, seen)
+    assert abs(e - e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(frc - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+    assert kernel.info()["precision_single"] == "fp64"
+
+
+def test_single_replica_wide_network_uses_a_cluster():
+    force = synthetic.make_force([600, 256, 128, 4], ["Tanh", "Tanh", "Circular"], 200, seed=31)
+    pos = synthetic.make_positions(200, 1, seed=32)[0]
+    e, frc, seen, kernel = run_single(force, pos, "double")
+    assert kernel.info()["cluster_size"] > 1
+    e_ref, f_ref = port.evaluate(force, seen)
+    assert abs(e - e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(frc - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+
+
+def test_include_flags():
+    force = synthetic.make_config("c2")
+    pos = synthetic.make_positions(7, 1)[0]
+    ctx = CudaContextBuffers(7, "double")
+    ctx.set_positions(pos)
+    kernel = CalcANNForce()
+    kernel.initialize(7, force)
+    kernel.execute(ctx, includeForces=False, includeEnergy=True)
+    torch.cuda.synchronize()
+    assert np.all(ctx.get_forces() == 0.0) and ctx.get_energy() > 0.0
+    ctx.clear()
+    kernel.execute(ctx, includeForces=True, includeEnergy=False)
+    torch.cuda.synchronize()
+    assert np.any(ctx.get_forces() != 0.0) and ctx.get_energy() == 0.0
+
+
+def test_copy_parameters_to_context():
+    """updateParametersInContext moves centre and k on the device (an empty stub in the reference:
+    ANN_ReferenceKernels.cpp:96-111, CudaANN_Kernels.cpp:371-395)."""
+    force = synthetic.make_config("c2")
+    pos = synthetic.make_positions(7, 1)[0]
+    ctx = CudaContextBuffers(7, "double")
+    ctx.set_positions(pos)
+    kernel = CalcANNForce()
+    kernel.initialize(7, force)
+    force.set_potential_center([1.25, -2.5])
+    force.set_force_constant(123.0)
+    kernel.copyParametersToContext(force)
+    kernel.execute(ctx)
+    torch.cuda.synchronize()
+    e_ref, f_ref = port.evaluate(force, ctx.positions_seen_by_kernels())
+    assert abs(ctx.get_energy() - e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(ctx.get_forces() - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+    # batched entry sees the update too
+    coords = torch.as_tensor(pos[None], device="cuda")
+    e, f = kernel.execute_batched(coords)
+    assert abs(e.item() - e_ref) <= 1e-11 * abs(e_ref)
+    force.set_potential_center([1.0, 2.0, 3.0])
+    with pytest.raises(_capi.ANNForceError):
+        kernel.copyParametersToContext(force)
+
+
+def test_single_replica_finite_differences():
+    """The reference's own integration check (test_ANN_package.cpp:175-180), central differences on the GPU energy."""
+    force, pos = cases.cartesian_12_4_4("Circular")
+    _, analytic, _, _ = run_single(force, pos, "double")
+    h = 1e-5
+    numeric = np.zeros_like(pos)
+    for a in range(pos.shape[0]):
+        for c in range(3):
+            p = pos.copy(); p[a, c] += h
+            m = pos.copy(); m[a, c] -= h
+            numeric[a, c] = -(run_single(force, p, "double")[0] - run_single(force, m, "double")[0]) / (2 * h)
+    assert np.abs(analytic - numeric).max() <= 1e-6 * max(1.0, np.abs(analytic).max())
+
+
+# ------------------------------------------------------------------------------------------------------
+# batched replicas
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CARTESIAN_GOLDEN)
+def test_batched_fp64_matches_golden(name):
+    force, pos, centers, energies, forces, _ = golden_io.load(name)
+    pos32 = pos.astype(np.float32)
+    cen32 = None if centers is None else centers.astype(np.float32)
+    exact = np.array_equal(pos32.astype(np.float64), pos) and (centers is None or np.array_equal(cen32.astype(np.float64), centers))
+    e, f, kernel = run_batched(force, pos32, cen32, precision="fp64")
+    if exact:
+        e_ref, f_ref = energies, forces
+    else:
+        e_ref, f_ref = port.evaluate(force, pos32.astype(np.float64), None if cen32 is None else cen32.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=1e-11)
+    assert max_norm_rel(f, f_ref) <= 1e-6     # forces leave the device as fp32
+
+
+@pytest.mark.parametrize("R", [1, 7, 8, 9, 257])
+@pytest.mark.parametrize("precision,e_tol,f_tol", [("fp64", 1e-11, 1e-6), ("fp32", 2e-5, F_RTOL)])
+def test_batched_ragged_replica_counts(R, precision, e_tol, f_tol):
+    """Ragged tiles, per-replica centres, a non-contiguous selection inside a larger system.
+    fp32 contractions: the stated tolerance is 2e-5 relative on the energy (cancellation in cv - centre,
+    SURVEY.md §7) and the north-star 1e-4 on forces."""
+    rng = np.random.default_rng(5)
+    atom_index = (rng.permutation(30)[:7] + 1).tolist()
+    force = synthetic.make_force([21, 40, 4], ["Tanh", "Circular"], 7, seed=6, atom_index=atom_index)
+    pos = synthetic.make_positions(30, R, seed=R)
+    cen = synthetic.make_centers(force, R, seed=R + 1)
+    e, f, kernel = run_batched(force, pos, cen, precision=precision)
+    assert kernel.info()["precision_batched"] == precision
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=e_tol)
+    assert max_norm_rel(f, f_ref) <= f_tol
+    sel = np.asarray(atom_index) - 1
+    mask = np.ones(30, dtype=bool); mask[sel] = False
+    assert np.all(f[:, mask, :] == 0.0)
+
+
+@pytest.mark.parametrize("config,R", [("c1", 64), ("c3", 256), ("c4", 96)])
+def test_batched_baseline_shapes_auto_precision(config, R):
+    cfg = synthetic.CONFIGS[config]
+    force = synthetic.make_config(config)
+    pos = synthetic.make_positions(cfg["atoms"], R)
+    cen = synthetic.make_centers(force, R)
+    e, f, kernel = run_batched(force, pos, cen, precision="auto")
+    assert kernel.info()["precision_batched"] == "fp64"      # AUTO keeps small networks in fp64
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=1e-11)         # far inside the 1e-6 bar
+    assert max_norm_rel(f, f_ref) <= 1e-6                    # far inside the 1e-4 bar
+
+
+def test_batched_host_entry_matches_device_entry():
+    force = synthetic.make_force([21, 40, 2], ["Tanh", "Tanh"], 7, seed=2, atom_index=[2, 3, 5, 7, 11, 13, 17])
+    pos = synthetic.make_positions(20, 37)
+    cen = synthetic.make_centers(force, 37)
+    e_d, f_d, _ = run_batched(force, pos, cen, precision="fp64")
+    e_h, f_h, _ = run_batched(force, pos, cen, precision="fp64", host=True)
+    np.testing.assert_array_equal(e_d, e_h)
+    np.testing.assert_array_equal(f_d, f_h)     # including zeros for the unselected atoms
+
+
+def test_batched_fp32_mid_size_network():
+    force = synthetic.make_config("c4")
+    pos = synthetic.make_positions(60, 40)
+    e, f, _ = run_batched(force, pos, None, precision="fp32")
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=2e-5)
+    assert max_norm_rel(f, f_ref) <= F_RTOL
+
+
+def test_wide_network_properties_and_sampled_parity():
+    """BASELINE config 5 shape (4500-512-512-8) at full width.  The oracle needs ~0.1 s per evaluation, so
+    parity is sampled on a few replicas and the rest is covered by size-independent properties:
+    translation invariance (centroid removal), zero net force, and exact linearity in the force constant."""
+    cfg = synthetic.CONFIGS["c5"]
+    force = synthetic.make_config("c5")
+    R = 24
+    pos = synthetic.make_positions(cfg["atoms"], R)
+    cen = synthetic.make_centers(force, R)
+    e, f, kernel = run_batched(force, pos, cen, precision="auto")
+    sample = [0, 11, 23]
+    e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
+    tol_e = 2e-5 if kernel.info()["precision_batched"] != "fp64" else 1e-10
+    np.testing.assert_allclose(e[sample], e_ref, rtol=tol_e)
+    assert max_norm_rel(f[sample], f_ref) <= F_RTOL
+    # zero net force per replica
+    assert np.abs(f.sum(axis=1)).max() <= 1e-3 * np.abs(f).max()
+    # translation invariance
+    shift = np.array([0.37, -1.2, 2.5], dtype=np.float32)
+    e2, f2, _ = run_batched(force, pos + shift, cen, precision="auto")
+    np.testing.assert_allclose(e2, e, rtol=1e-4)
+    # linear in k
+    force.set_force_constant(2.0 * force.get_force_constant())
+    e3, f3, _ = run_batched(force, pos, cen, precision="auto")
+    np.testing.assert_allclose(e3, 2.0 * e, rtol=1e-6)
+    assert max_norm_rel(f3, 2.0 * f) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# error behaviour
+# ------------------------------------------------------------------------------------------------------
+def test_errors_are_reported_not_swallowed():
+    force = synthetic.make_config("c2")
+    kernel = CalcANNForce()
+    with pytest.raises(RuntimeError):
+        kernel.execute_batched(torch.zeros(1, 7, 3, device="cuda"))       # before initialize()
+    with pytest.raises(_capi.ANNForceError):
+        kernel.initialize(5, force)                                        # atom index 7 outside a 5-atom system
+    kernel.initialize(7, force)
+    with pytest.raises(_capi.ANNForceError):
+        kernel.execute_batched(torch.zeros(2, 6, 3, device="cuda"))        # fewer atoms per replica than the system
+    # the legacy CUDA kernel threw for dihedral input (CudaANN_Kernels.cpp:257-260); so does this one, for now
+    dih, _ = cases.dihedral_4_4_4("Tanh")
+    with pytest.raises(_capi.ANNForceError):
+        CalcANNForce().initialize(6, dih)
