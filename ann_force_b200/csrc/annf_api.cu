@@ -297,7 +297,7 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     int cl = 1;
     while (cl < 8 && weight_bytes / cl > 48.0 * 1024) cl *= 2;
     h->cluster_size = cl;
-    if (single_smem_bytes(net) > 227 * 1024) {
+    if (single_smem_bytes(net) > 226 * 1024) {
         release(h);
         return fail(ANNF_ERR_UNSUPPORTED, "network too large for the single-replica kernel's shared memory (%zu bytes)",
                     single_smem_bytes(net));

@@ -315,7 +315,7 @@ static cudaError_t launch_t(const BatchedArgs& args, size_t smem, cudaStream_t s
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(annf_batched_kernel<T, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t err = cudaFuncSetAttribute(annf_batched_kernel<T, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (err != cudaSuccess) return err;
         configured[dev] = true;
     }

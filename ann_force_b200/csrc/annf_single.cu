@@ -291,7 +291,7 @@ cudaError_t prepare_single(const NetView& net, int cluster_size) {
     // function attributes are per device, not per handle: always ask for the architectural maximum so
     // that handles of different sizes can coexist
     (void) net;
-    cudaError_t err = cudaFuncSetAttribute(annf_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t err = cudaFuncSetAttribute(annf_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (err != cudaSuccess) return err;
     if (cluster_size > 8)
         err = cudaFuncSetAttribute(annf_single_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
