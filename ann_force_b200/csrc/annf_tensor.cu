@@ -1,24 +1,795 @@
-// Layer-wise tensor-core path (tcgen05, 3xTF32) for wide layers — placeholder until the kernels land.
+// Layer-wise tensor-core path for wide networks (sm_100a): tcgen05.mma kind::tf32 with the 3xTF32
+// split, TMA-fed shared-memory pipeline, fp32 accumulators in TMEM, fused epilogues.
+//
+// For a batch of R replicas the hidden layers are real dense contractions
+//     forward   X_{l+1} = act(X_l  * W_l^T + b_l)        M = R, N = n_{l+1}, K = n_l
+//     backward  D_l     = (D_{l+1} * W_l) (.) act'(X_l)   M = R, N = n_l,     K = n_{l+1}
+// (ANN_ReferenceKernels.cpp:193-209 and :340-354 with the replica index as the GEMM M dimension).
+// Every fp32 operand v is stored as a TF32 pair  hi = rna_tf32(v), lo = rna_tf32(v - hi)  so that
+//     v*w ~= hi_v*hi_w + hi_v*lo_w + lo_v*hi_w      (three tcgen05.mma per K-step, error ~2^-22)
+// Weights are split once at plan creation (both W and W^T, K-major for the tensor core); activations
+// are split by the epilogue that produces them.  The tiny output layer, the umbrella energy and its
+// gradient stay fp64 in a SIMT "head" kernel; gather/centre ("prep") is a bandwidth-bound SIMT kernel;
+// the centring Jacobian is one mean per component, computed ahead of the last backward contraction
+// ("colmean"), whose epilogue then writes the forces directly.
+//
+// GEMM kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0  : TMA producer   - cp.async.bulk.tensor.2d of A_hi, A_lo, B_hi, B_lo (128B swizzle) per stage
+//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2-5: epilogue      - tcgen05.ld TMEM -> registers -> bias / tanh / tanh' -> hi/lo stores
+// Accumulation: the tensor core's fp32 accumulator does not round to nearest, so a K = 4500 chain in
+// TMEM costs ~30x the error of the products themselves (measured).  The K loop is therefore cut into
+// chunks of kChunk K-blocks: a chunk accumulates in one of two TMEM buffers while the epilogue warps
+// drain the other one into fp32 REGISTER accumulators with round-to-nearest adds ("promotion").
+// Split-K: S CTAs of one cluster (cluster dims 1x1xS) each take a K-range, park their partial tile in
+// their own shared memory, and after one cluster barrier every CTA reduces a 128/S-row slice over
+// all peers through DSMEM in a fixed order (deterministic), then runs the epilogue on it.
+#include <cooperative_groups.h>
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
 #include "annf_common.cuh"
 #include "annf_profiler.h"
 
+namespace cg = cooperative_groups;
+
 namespace annf {
 
-struct TensorPlan {};
+constexpr int BM = 128;               // replicas per tile = UMMA M
+constexpr int BK = 32;                // fp32 elements per K-block = 128 bytes = one swizzle span
+constexpr int UMMA_K = 8;             // tf32: 32 bytes per instruction along K
+constexpr int kGemmThreads = 192;
 
-TensorPlan* tensor_plan_create(const NetView&, const std::vector<std::vector<double>>&, std::string* why_not) {
-    if (why_not) *why_not = "tensor-core path not built into this library yet";
-    return nullptr;
+constexpr int kChunk = 2;             // K-blocks accumulated in TMEM between promotions (K = 64: 24 chained MMAs)
+
+enum { EPI_STORE = 0, EPI_BIAS_TANH = 1, EPI_BIAS_LINEAR = 2, EPI_TANH_GRAD = 3, EPI_LINEAR_GRAD = 4, EPI_FORCE = 5 };
+
+struct GemmParams {
+    int M, N, K;
+    int epi;
+    const float* bias;                // [N]               (EPI_BIAS_*)
+    const float* aux_hi;              // [M][ld_aux] activations of the layer being differentiated (EPI_TANH_GRAD)
+    const float* aux_lo;
+    int ld_aux;
+    float* out_hi;                    // [M][ld_out]  (EPI_STORE: the plain fp32 result; EPI_FORCE: forces [M][atoms][3])
+    float* out_lo;
+    int ld_out;                       //              (EPI_FORCE: 3 * atoms_per_replica)
+    const float* row_mean;            // [M][4] mean input-gradient per component (EPI_FORCE)
+    const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
+    float neg_inv_scale;              // -1 / scaling_factor (EPI_FORCE)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, N = BN, K = 8 (tf32), issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-void tensor_plan_destroy(TensorPlan* plan) { delete plan; }
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO<<16 | SBO<<32 | version=1<<46 | SWIZZLE_128B=2<<61)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    return (uint64_t) ((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+}
 
-cudaError_t tensor_plan_run(TensorPlan*, Profiler*, const NetView&, int, const float*, int, const float*, float*, double*,
-                            cudaStream_t, long long*) {
-    return cudaErrorNotSupported;
+__device__ __forceinline__ float tf32_round(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    hi = tf32_round(v);
+    lo = tf32_round(v - hi);
+}
+
+template <int BN> struct GemmCfg {
+    static constexpr int kStageBytes = (2 * BM + 2 * BN) * BK * 4;
+    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int kStagingLd = BN + 4;                                   // fp32 elements, padded against bank conflicts
+    static constexpr int kStagingBytes = BM * kStagingLd * 4;
+    static constexpr int kDataBytes = kStageBytes * kStages > kStagingBytes ? kStageBytes * kStages : kStagingBytes;
+    static constexpr int kSmemBytes = kDataBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// One epilogue element group: 4 consecutive columns of one output row.
+__device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int n, float4 v) {
+    if (p.epi == EPI_STORE) {
+        *reinterpret_cast<float4*>(p.out_hi + (size_t) m * p.ld_out + n) = v;
+        return;
+    }
+    if (p.epi == EPI_FORCE) {
+        // column n = 3 * atom + component: F = -(g - mean_component) / s   (ANN_ReferenceKernels.cpp:397-410,
+        // the O(A^2) Jacobian loop collapsed into one mean per component)
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(p.row_mean) + m);
+        const float mean[3] = {mu.x, mu.y, mu.z};
+        const float g[4] = {v.x, v.y, v.z, v.w};
+        float f[4];
+        int c = n % 3;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            f[j] = (g[j] - mean[c]) * p.neg_inv_scale;
+            c = c == 2 ? 0 : c + 1;
+        }
+        float* row = p.out_hi + (size_t) m * p.ld_out;
+        if (p.sel_atoms == nullptr) {
+            *reinterpret_cast<float4*>(row + n) = make_float4(f[0], f[1], f[2], f[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = n + j, atom = e / 3;
+                row[(size_t) __ldg(p.sel_atoms + atom) * 3 + (e - 3 * atom)] = f[j];
+            }
+        }
+        return;
+    }
+    if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (p.epi == EPI_BIAS_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+    } else if (p.epi == EPI_TANH_GRAD) {
+        const float4 ah = __ldg(reinterpret_cast<const float4*>(p.aux_hi + (size_t) m * p.ld_aux + n));
+        const float4 al = __ldg(reinterpret_cast<const float4*>(p.aux_lo + (size_t) m * p.ld_aux + n));
+        const float a0 = ah.x + al.x, a1 = ah.y + al.y, a2 = ah.z + al.z, a3 = ah.w + al.w;
+        v.x *= (1.f - a0 * a0); v.y *= (1.f - a1 * a1); v.z *= (1.f - a2 * a2); v.w *= (1.f - a3 * a3);
+    }
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(p.out_hi + (size_t) m * p.ld_out + n) = hi;
+    *reinterpret_cast<float4*>(p.out_lo + (size_t) m * p.ld_out + n) = lo;
+}
+
+template <int BN, int S>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+              const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle atoms (TMA and UMMA must agree on address bits 7..9)
+    unsigned char* data = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(data + Cfg::kDataBytes);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + kStages;
+    uint64_t* bar_acc_full = bars + 2 * kStages;
+    uint64_t* bar_acc_empty = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int rank = S > 1 ? (int) blockIdx.z : 0;
+    const int kb_total = (p.K + BK - 1) / BK;
+    const int kb0 = (int) ((long long) kb_total * rank / S), kb1 = (int) ((long long) kb_total * (rank + 1) / S);
+    const int num_kb = kb1 - kb0;
+    const int num_chunks = (num_kb + kChunk - 1) / kChunk;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(smem_u32(&bar_acc_full[b]), 1);
+            mbar_init(smem_u32(&bar_acc_empty[b]), 4);            // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; i++) {
+                const int s = i % kStages;
+                const uint32_t ph = (uint32_t) (i / kStages) & 1u;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                      // slot free
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
+                const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
+                const int kc = (kb0 + i) * BK;
+                tma_load_2d(base, &tm_a_hi, full, kc, m0);
+                tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
+                tma_load_2d(base + 2 * BM * BK * 4, &tm_b_hi, full, kc, n0);
+                tma_load_2d(base + 2 * BM * BK * 4 + BN * BK * 4, &tm_b_lo, full, kc, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread).  Chunk c accumulates into TMEM buffer c & 1. =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            int i = 0;
+            for (int c = 0; c < num_chunks; c++) {
+                const int buf = c & 1;
+                const uint32_t use = (uint32_t) (c >> 1);
+                mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);        // epilogue drained this buffer
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * BN);
+                const int i_end = min(num_kb, (c + 1) * kChunk);
+                bool first = true;
+                for (; i < i_end; i++) {
+                    const int s = i % kStages;
+                    const uint32_t ph = (uint32_t) (i / kStages) & 1u;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);                         // TMA bytes landed
+                    tcgen05_fence_after();
+                    const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
+                    const uint32_t a_hi = base, a_lo = base + BM * BK * 4;
+                    const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + BN * BK * 4;
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                        const uint32_t off = kk * UMMA_K * 4;                      // 32 bytes along K inside the swizzle span
+                        const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
+                        const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
+                        umma_tf32(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);     // small terms first
+                        umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                        first = false;
+                    }
+                    umma_commit(smem_u32(&bar_empty[s]));                          // frees the slot when these MMAs retire
+                }
+                umma_commit(smem_u32(&bar_acc_full[buf]));                         // chunk complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: promote TMEM chunks into fp32 registers (round-to-nearest adds) =====
+        const int q = warp & 3;                                                    // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        float acc[BN];
+#pragma unroll
+        for (int j = 0; j < BN; j++) acc[j] = 0.f;
+        for (int c = 0; c < num_chunks; c++) {
+            const int buf = c & 1;
+            const uint32_t use = (uint32_t) (c >> 1);
+            mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < BN / 32; cc++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (buf * BN + cc * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[cc * 32 + j] += __uint_as_float(r[j]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_acc_empty[buf])) : "memory");
+        }
+        if (S == 1) {
+            const int m = m0 + row;
+            if (m < p.M) {
+#pragma unroll
+                for (int j = 0; j < BN; j += 4) {
+                    const int n = n0 + j;
+                    if (n < p.N) epilogue_store4(p, m, n, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                }
+            }
+        } else {
+            // park the partial tile (all TMA loads have landed and been consumed: the stage buffers are free)
+            float* dst = reinterpret_cast<float*>(data) + (size_t) row * Cfg::kStagingLd;
+#pragma unroll
+            for (int j = 0; j < BN; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+    }
+
+    if (S > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();                                                            // every partial tile is parked
+        if (warp >= 2) {
+            constexpr int kRows = BM / S;                                          // rows this CTA reduces
+            constexpr int kVecPerRow = BN / 4;
+            const int t = threadIdx.x - 64;                                        // 0..127
+            float* staging = reinterpret_cast<float*>(data);
+            const float* peer[S];
+#pragma unroll
+            for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, r);
+            for (int v = t; v < kRows * kVecPerRow; v += 128) {
+                const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < S; r++) {                                      // fixed order: deterministic
+                    const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
+                    sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+                }
+                const int m = m0 + row, n = n0 + col;
+                if (m < p.M && n < p.N) epilogue_store4(p, m, n, sum);
+            }
+        }
+        cluster.sync();                                                            // nobody leaves while peers still read
+    } else {
+        __syncthreads();
+    }
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT companions
+// ------------------------------------------------------------------------------------------------
+// prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), centroid in fp64, write the TF32 pair.
+__global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
+                                                  float* __restrict__ x_hi, float* __restrict__ x_lo, int ld) {
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = net.n_sel;
+    const float* base = coords + (size_t) r * N * 3;
+    const double inv_scale = 1.0 / net.scale;
+    __shared__ double red[8][3];
+    __shared__ double com[3];
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < A; i += 256) {
+        const float* p = base + (size_t) net.sel_atoms[i] * 3;
+        s[0] += (double) __ldg(p); s[1] += (double) __ldg(p + 1); s[2] += (double) __ldg(p + 2);
+    }
+    for (int c = 0; c < 3; c++) s[c] = warp_sum(s[c]);
+    if (lane == 0) { red[warp][0] = s[0]; red[warp][1] = s[1]; red[warp][2] = s[2]; }
+    __syncthreads();
+    if (tid < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += red[w][tid];
+        com[tid] = t / A;                                   // centroid of the unscaled coordinates
+    }
+    __syncthreads();
+    for (int i = tid; i < 3 * A; i += 256) {
+        const int atom = i / 3, c = i - 3 * atom;
+        const double v = ((double) __ldg(base + (size_t) net.sel_atoms[atom] * 3 + c) - com[c]) * inv_scale;
+        float hi, lo;
+        split_tf32((float) v, hi, lo);
+        x_hi[(size_t) r * ld + i] = hi;
+        x_lo[(size_t) r * ld + i] = lo;
+    }
+}
+
+// head: output layer forward (fp64 accumulate), umbrella energy + gradient (output_head), and the
+// backward contraction through the output connection, fused with act'() of the last hidden layer.
+// The output-connection weights sit in shared memory; one warp per replica, kHeadReplicas per CTA.
+constexpr int kHeadReplicas = 8;
+__global__ void __launch_bounds__(256) head_kernel(NetView net, int R, const float* __restrict__ centers,
+                                                  const float* __restrict__ a_hi, const float* __restrict__ a_lo, int ld,
+                                                  float* __restrict__ d_hi, float* __restrict__ d_lo, double* __restrict__ energies) {
+    extern __shared__ double w_s[];                         // [nL][nH]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = net.L, nH = net.nodes[L - 2], nL = net.nodes[L - 1];
+    __shared__ double zs[kHeadReplicas][64], dzs[kHeadReplicas][64], cen[kHeadReplicas][64];
+    const double* W = net.W64 + net.w_off[L - 2];
+    const double* b = net.b64 + net.b_off[L - 2];
+    for (int i = threadIdx.x; i < nL * nH; i += 256) w_s[i] = __ldg(W + i);
+    __syncthreads();
+    const int r = blockIdx.x * kHeadReplicas + warp;
+    if (r >= R) return;
+    const float* ah = a_hi + (size_t) r * ld;
+    const float* al = a_lo + (size_t) r * ld;
+    for (int j = 0; j < nL; j++) {
+        double acc = 0.0;
+        for (int m = lane; m < nH; m += 32) acc = fma(w_s[j * nH + m], (double) ah[m] + (double) al[m], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) zs[warp][j] = acc + b[j];
+    }
+    for (int c = lane; c < net.num_center; c += 32)
+        cen[warp][c] = centers ? (double) centers[(size_t) r * net.num_center + c] : net.center[c];
+    __syncwarp();
+    if (lane == 0) energies[r] = output_head(net.types[L - 2], nL, zs[warp], 1, cen[warp], *net.k_dev, dzs[warp], 1);
+    __syncwarp();
+    const int hidden_type = net.types[L - 3];
+    for (int m = lane; m < nH; m += 32) {
+        double acc = 0.0;
+        for (int j = 0; j < nL; j++) acc = fma(w_s[j * nH + m], dzs[warp][j], acc);
+        if (hidden_type == ANNF_TANH) {
+            const double a = (double) ah[m] + (double) al[m];
+            acc *= (1.0 - a * a);
+        }
+        float hi, lo;
+        split_tf32((float) acc, hi, lo);
+        d_hi[(size_t) r * ld + m] = hi;
+        d_lo[(size_t) r * ld + m] = lo;
+    }
+}
+
+// colmean: mean over atoms of the input gradient, per replica and component, WITHOUT forming the gradient:
+//   (1/A) sum_i g[3i+c] = (1/A) sum_k D1[k] * (sum_i W0[k][3i+c])     (wsum precomputed at plan creation)
+// This is the Jacobian term of centroid removal (ANN_ReferenceKernels.cpp:402-406); knowing it before the last
+// backward contraction lets that GEMM's epilogue write the forces directly.  One warp per replica.
+__global__ void __launch_bounds__(256) colmean_kernel(int R, int K, int A, const float* __restrict__ d_hi,
+                                                     const float* __restrict__ d_lo, int ld, const double* __restrict__ wsum,
+                                                     float* __restrict__ row_mean) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= R) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const double d = (double) d_hi[(size_t) r * ld + k] + (double) d_lo[(size_t) r * ld + k];
+        s0 = fma(d, __ldg(wsum + k), s0);
+        s1 = fma(d, __ldg(wsum + K + k), s1);
+        s2 = fma(d, __ldg(wsum + 2 * K + k), s2);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0)
+        *reinterpret_cast<float4*>(row_mean + (size_t) r * 4) = make_float4((float) (s0 / A), (float) (s1 / A), (float) (s2 / A), 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: plan
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &res) == cudaSuccess &&
+            res == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// [rows][cols] fp32, row stride ld elements; box = 32 columns x box_rows rows, 128B swizzle, zero OOB fill
+static bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t) cols, (cuuint64_t) rows};
+    cuuint64_t strides[1] = {(cuuint64_t) ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t) BK, (cuuint32_t) box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct GemmOp {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    GemmParams p;
+    int bn;
+    char name[48];
+};
+
+struct TensorPlan {
+    int L = 0;
+    int nodes[kMaxLayers];
+    int types[kMaxLayers];
+    int ld[kMaxLayers];
+    int sm_count = 148;
+    int cap = 0;                                    // replica capacity of the activation buffers
+    // weights (TF32 pairs), forward [n_{l+1}][ld(n_l)] and transposed [n_l][ld(n_{l+1})], l = 0..L-3
+    float *w_hi[kMaxLayers] = {}, *w_lo[kMaxLayers] = {}, *wt_hi[kMaxLayers] = {}, *wt_lo[kMaxLayers] = {}, *bias[kMaxLayers] = {};
+    // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as TF32 pairs; G0 plain
+    float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {}, *row_mean = nullptr;
+    double* wsum = nullptr;                         // [3][n_1]: sum over atoms of W_0[k][3i+c]
+    bool sel_identity = false;                      // selection is atoms 0..A-1 in order
+    std::vector<GemmOp> fwd, bwd;
+};
+
+static void free_activations(TensorPlan* t) {
+    for (int l = 0; l < kMaxLayers; l++) {
+        cudaFree(t->x_hi[l]); cudaFree(t->x_lo[l]); cudaFree(t->d_hi[l]); cudaFree(t->d_lo[l]);
+        t->x_hi[l] = t->x_lo[l] = t->d_hi[l] = t->d_lo[l] = nullptr;
+    }
+    cudaFree(t->row_mean);
+    t->row_mean = nullptr;
+    t->cap = 0;
+}
+
+void tensor_plan_destroy(TensorPlan* t) {
+    if (!t) return;
+    free_activations(t);
+    for (int l = 0; l < kMaxLayers; l++) {
+        cudaFree(t->w_hi[l]); cudaFree(t->w_lo[l]); cudaFree(t->wt_hi[l]); cudaFree(t->wt_lo[l]); cudaFree(t->bias[l]);
+    }
+    cudaFree(t->wsum);
+    delete t;
+}
+
+static float host_tf32(float v) {          // round-to-nearest, ties away from zero on the 13 dropped bits (cvt.rna)
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return v;
+    u += 0x1000u;
+    u &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+static cudaError_t upload_pair(const std::vector<float>& src, float** hi, float** lo) {
+    std::vector<float> h(src.size()), l(src.size());
+    for (size_t i = 0; i < src.size(); i++) {
+        h[i] = host_tf32(src[i]);
+        l[i] = host_tf32(src[i] - h[i]);
+    }
+    cudaError_t err = cudaMalloc((void**) hi, sizeof(float) * src.size());
+    if (err != cudaSuccess) return err;
+    err = cudaMalloc((void**) lo, sizeof(float) * src.size());
+    if (err != cudaSuccess) return err;
+    err = cudaMemcpy(*hi, h.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return err;
+    return cudaMemcpy(*lo, l.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice);
+}
+
+TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, std::string* why_not) {
+    auto no = [&](const char* msg) { if (why_not) *why_not = msg; return (TensorPlan*) nullptr; };
+    const int L = net.L;
+    if (net.input_type != ANNF_INPUT_CARTESIAN) return no("only Cartesian input is on the tensor-core path");
+    if (L < 3) return no("no hidden layer");
+    if (net.nodes[L - 1] > 64 || net.num_center > 64) return no("output layer wider than 64 nodes");
+    for (int l = 0; l + 2 < L; l++)
+        if (net.types[l] != ANNF_TANH && net.types[l] != ANNF_LINEAR) return no("hidden layers must be Tanh or Linear");
+    for (int l = 0; l + 1 < L; l++)
+        if (net.nodes[l] % 4 != 0) return no("layer widths (except the output layer) must be multiples of 4");
+    for (int l = 1; l + 1 < L; l++)
+        if (net.nodes[l] < 64) return no("hidden layers narrower than 64 nodes are not a dense contraction worth the tensor pipe");
+    if (!encode_fn()) return no("cuTensorMapEncodeTiled is not available from this driver");
+    if ((size_t) net.nodes[L - 1] * net.nodes[L - 2] * sizeof(double) > 160 * 1024)
+        return no("output connection too large for the head kernel's shared memory");
+    if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+        return no("cannot configure the head kernel");
+    TensorPlan* t = new TensorPlan();
+    t->L = L;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    for (int l = 0; l < L; l++) { t->nodes[l] = net.nodes[l]; t->ld[l] = round_up(net.nodes[l], 4); }
+    for (int l = 0; l + 1 < L; l++) t->types[l] = net.types[l];
+    for (int l = 0; l + 2 < L; l++) {
+        const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+        std::vector<float> w((size_t) n_out * t->ld[l], 0.f), wt((size_t) n_in * t->ld[l + 1], 0.f);
+        for (int j = 0; j < n_out; j++)
+            for (int i = 0; i < n_in; i++) {
+                const float v = (float) coeff[l][(size_t) j * n_in + i];
+                w[(size_t) j * t->ld[l] + i] = v;
+                wt[(size_t) i * t->ld[l + 1] + j] = v;
+            }
+        if (upload_pair(w, &t->w_hi[l], &t->w_lo[l]) != cudaSuccess || upload_pair(wt, &t->wt_hi[l], &t->wt_lo[l]) != cudaSuccess) {
+            tensor_plan_destroy(t);
+            return no("out of device memory for the tensor-core weight copies");
+        }
+    }
+    // fp32 biases live in NetView::b32 already
+    {   // per-component column sums of W_0 for the centring Jacobian (colmean_kernel)
+        const int n0 = net.nodes[0], n1 = net.nodes[1];
+        std::vector<double> wsum((size_t) 3 * n1, 0.0);
+        for (int k = 0; k < n1; k++)
+            for (int i = 0; i < n0; i++) wsum[(size_t) (i % 3) * n1 + k] += coeff[0][(size_t) k * n0 + i];
+        if (cudaMalloc((void**) &t->wsum, sizeof(double) * wsum.size()) != cudaSuccess ||
+            cudaMemcpy(t->wsum, wsum.data(), sizeof(double) * wsum.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            tensor_plan_destroy(t);
+            return no("out of device memory");
+        }
+        std::vector<int> sel(net.n_sel);
+        cudaMemcpy(sel.data(), net.sel_atoms, sizeof(int) * net.n_sel, cudaMemcpyDeviceToHost);
+        t->sel_identity = true;
+        for (int i = 0; i < net.n_sel; i++) t->sel_identity = t->sel_identity && sel[i] == i;
+    }
+    return t;
+}
+
+static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
+    if (R <= t->cap) return cudaSuccess;
+    free_activations(t);
+    const int cap = round_up(R, BM);
+    const int L = t->L;
+    auto alloc = [&](float** p, int ld) {
+        cudaError_t e = cudaMalloc((void**) p, sizeof(float) * (size_t) cap * ld);
+        if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(float) * (size_t) cap * ld);
+        return e;
+    };
+    cudaError_t err = cudaSuccess;
+    for (int l = 0; l + 1 < L && err == cudaSuccess; l++) {
+        err = alloc(&t->x_hi[l], t->ld[l]);
+        if (err == cudaSuccess) err = alloc(&t->x_lo[l], t->ld[l]);
+        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_hi[l], t->ld[l]);
+        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], t->ld[l]);
+    }
+    if (err == cudaSuccess) err = alloc(&t->row_mean, 4);
+    if (err != cudaSuccess) return err;
+    t->cap = cap;
+    t->fwd.clear();
+    t->bwd.clear();
+    for (int l = 0; l + 2 < L; l++) {                 // forward: X_{l+1} = act(X_l W_l^T + b)
+        GemmOp op;
+        memset(&op, 0, sizeof(op));
+        op.bn = 128;
+        const int K = t->nodes[l], N = t->nodes[l + 1];
+        bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, t->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, t->ld[l], BM) &&
+                  make_map(&op.b_hi, t->w_hi[l], N, K, t->ld[l], op.bn) && make_map(&op.b_lo, t->w_lo[l], N, K, t->ld[l], op.bn);
+        if (!ok) return cudaErrorInvalidValue;
+        op.p.N = N; op.p.K = K;
+        op.p.epi = t->types[l] == ANNF_TANH ? EPI_BIAS_TANH : EPI_BIAS_LINEAR;
+        op.p.bias = net.b32 + net.b_off[l];
+        op.p.out_hi = t->x_hi[l + 1]; op.p.out_lo = t->x_lo[l + 1]; op.p.ld_out = t->ld[l + 1];
+        snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] fwd%d tf32x3", N, K, l);
+        t->fwd.push_back(op);
+    }
+    for (int l = L - 3; l >= 0; l--) {                // backward: D_l = (D_{l+1} W_l) (.) act'(X_l);  l = 0 -> G0
+        GemmOp op;
+        memset(&op, 0, sizeof(op));
+        op.bn = 128;
+        const int K = t->nodes[l + 1], N = t->nodes[l];
+        bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, t->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, t->ld[l + 1], BM) &&
+                  make_map(&op.b_hi, t->wt_hi[l], N, K, t->ld[l + 1], op.bn) && make_map(&op.b_lo, t->wt_lo[l], N, K, t->ld[l + 1], op.bn);
+        if (!ok) return cudaErrorInvalidValue;
+        op.p.N = N; op.p.K = K;
+        if (l == 0) {
+            op.p.epi = EPI_FORCE;                     // out_hi / ld_out / sel_atoms are per call (launch_gemm)
+            op.p.row_mean = t->row_mean;
+            op.p.neg_inv_scale = (float) (-1.0 / net.scale);
+        } else {
+            op.p.epi = t->types[l - 1] == ANNF_TANH ? EPI_TANH_GRAD : EPI_LINEAR_GRAD;
+            op.p.aux_hi = t->x_hi[l]; op.p.aux_lo = t->x_lo[l]; op.p.ld_aux = t->ld[l];
+            op.p.out_hi = t->d_hi[l]; op.p.out_lo = t->d_lo[l]; op.p.ld_out = t->ld[l];
+        }
+        snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] bwd%d tf32x3", N, K, l);
+        t->bwd.push_back(op);
+    }
+    return cudaSuccess;
+}
+
+template <int BN, int S>
+static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
+        if (err != cudaSuccess) return err;
+        configured[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, S);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = GemmCfg<BN>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = S;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm3x_kernel<BN, S>, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p);
+}
+
+static int pick_split(int tiles, int k_blocks, int sm_count) {
+    int s = 1;
+    while (s < 8 && tiles * (s * 2) <= sm_count + sm_count / 8 && k_blocks / (s * 2) >= 4) s *= 2;
+    return s;
+}
+
+static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStream_t stream, const NetView& net,
+                               float* forces, int atoms_per_replica) {
+    GemmParams p = op.p;
+    p.M = R;
+    if (p.epi == EPI_FORCE) {
+        p.out_hi = forces;
+        p.ld_out = 3 * atoms_per_replica;
+        const bool vec_ok = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(forces) & 15) == 0;
+        p.sel_atoms = vec_ok ? nullptr : net.sel_atoms;
+    }
+    const int tiles = ((p.N + 127) / 128) * ((R + BM - 1) / BM);
+    const int s = pick_split(tiles, (p.K + BK - 1) / BK, t->sm_count);
+    switch (s) {
+    case 8: return launch_gemm_t<128, 8>(op, p, stream);
+    case 4: return launch_gemm_t<128, 4>(op, p, stream);
+    case 2: return launch_gemm_t<128, 2>(op, p, stream);
+    default: return launch_gemm_t<128, 1>(op, p, stream);
+    }
+}
+
+cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, int R, const float* coords,
+                            int atoms_per_replica, const float* centers, float* forces, double* energies,
+                            cudaStream_t stream, long long* launches) {
+    cudaError_t err = ensure_capacity(t, net, R);
+    if (err != cudaSuccess) return err;
+    const int L = t->L;
+    char name[64];
+    auto timed = [&](const char* nm, auto&& fn) {
+        prof->begin(nm, stream);
+        cudaError_t e = fn();
+        prof->end(stream);
+        if (launches) (*launches)++;
+        return e;
+    };
+    err = timed("prep_kernel", [&] {
+        prep_kernel<<<R, 256, 0, stream>>>(net, R, coords, atoms_per_replica, t->x_hi[0], t->x_lo[0], t->ld[0]);
+        return cudaGetLastError();
+    });
+    if (err != cudaSuccess) return err;
+    for (const GemmOp& op : t->fwd) {
+        snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
+        err = timed(name, [&] { return launch_gemm(t, op, R, stream, net, nullptr, 0); });
+        if (err != cudaSuccess) return err;
+    }
+    err = timed("head_kernel", [&] {
+        const size_t smem = sizeof(double) * (size_t) t->nodes[L - 1] * t->nodes[L - 2];
+        head_kernel<<<(R + kHeadReplicas - 1) / kHeadReplicas, 256, smem, stream>>>(
+            net, R, centers, t->x_hi[L - 2], t->x_lo[L - 2], t->ld[L - 2], t->d_hi[L - 2], t->d_lo[L - 2], energies);
+        return cudaGetLastError();
+    });
+    if (err != cudaSuccess) return err;
+    for (const GemmOp& op : t->bwd) {
+        if (op.p.epi == EPI_FORCE) {
+            err = timed("colmean_kernel", [&] {
+                colmean_kernel<<<(R + 7) / 8, 256, 0, stream>>>(R, t->nodes[1], net.n_sel, t->d_hi[1], t->d_lo[1], t->ld[1],
+                                                                 t->wsum, t->row_mean);
+                return cudaGetLastError();
+            });
+            if (err != cudaSuccess) return err;
+        }
+        snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
+        err = timed(name, [&] { return launch_gemm(t, op, R, stream, net, forces, atoms_per_replica); });
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace annf

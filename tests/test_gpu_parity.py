@@ -230,6 +230,7 @@ def test_wide_network_properties_and_sampled_parity():
     pos = synthetic.make_positions(cfg["atoms"], R)
     cen = synthetic.make_centers(force, R)
     e, f, kernel = run_batched(force, pos, cen, precision="auto")
+    assert kernel.info()["batched_path"] == "tensor" and kernel.info()["precision_batched"] == "tf32x3"
     sample = [0, 11, 23]
     e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
     tol_e = 2e-5 if kernel.info()["precision_batched"] != "fp64" else 1e-10
@@ -246,6 +247,42 @@ def test_wide_network_properties_and_sampled_parity():
     e3, f3, _ = run_batched(force, pos, cen, precision="auto")
     np.testing.assert_allclose(e3, 2.0 * e, rtol=1e-6)
     assert max_norm_rel(f3, 2.0 * f) <= 1e-5
+
+
+@pytest.mark.parametrize("nodes,types,R", [
+    ([300, 128, 64, 4], ["Tanh", "Tanh", "Circular"], 200),      # K not a multiple of 32, N < tile, ragged M, split-K 2
+    ([300, 128, 64, 4], ["Linear", "Tanh", "Tanh"], 130),        # Linear hidden layer
+    ([600, 512, 128, 4], ["Tanh", "Tanh", "Tanh"], 64),          # split-K 4 (19 and 16 K-blocks), no split backward
+    ([300, 128, 4], ["Tanh", "Softmax"], 1),                     # one hidden layer, single replica, Softmax head
+    ([1536, 256, 256, 2], ["Tanh", "Tanh", "Linear"], 384),      # three M tiles
+])
+def test_tensor_core_path_matches_oracle(nodes, types, R):
+    """tcgen05 3xTF32 path.  Stated tolerance (BASELINE config 5 "tensor-core dense-contraction path, stated
+    tolerance"), worst replica: energy 2e-5 relative for Tanh/Linear/Softmax outputs and 2e-4 for Circular outputs
+    (an angle error d_theta costs k*Delta*d_theta, and Delta reaches pi); forces 1e-4 relative max-norm.
+    The MEDIAN energy error must stay below 3e-6: a lost hi*lo term would put it near 5e-4."""
+    atoms = nodes[0] // 3
+    force = synthetic.make_force(nodes, types, atoms, seed=41)
+    pos = synthetic.make_positions(atoms + 3, R, seed=42)
+    cen = synthetic.make_centers(force, R, seed=43)
+    e, f, kernel = run_batched(force, pos, cen, precision="tf32x3")
+    assert kernel.info()["batched_path"] == "tensor"
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    rel = np.abs(e - e_ref) / np.abs(e_ref)
+    assert rel.max() <= (2e-4 if types[-1] == "Circular" else 2e-5), rel.max()
+    assert np.median(rel) <= 3e-6, np.median(rel)
+    assert max_norm_rel(f, f_ref) <= F_RTOL
+    assert np.all(f[:, atoms:, :] == 0.0)
+    # run-to-run determinism (split-K reduces in a fixed order)
+    e2, f2, _ = run_batched(force, pos, cen, precision="tf32x3")
+    np.testing.assert_array_equal(e, e2)
+    np.testing.assert_array_equal(f, f2)
+
+
+def test_tensor_core_path_rejects_what_it_cannot_do():
+    force = synthetic.make_force([21, 40, 4], ["Tanh", "Circular"], 7, seed=1)
+    with pytest.raises(_capi.ANNForceError):
+        CalcANNForce(precision="tf32x3").initialize(7, force)      # 21 and 40 are not dense-contraction shapes
 
 
 # ------------------------------------------------------------------------------------------------------
