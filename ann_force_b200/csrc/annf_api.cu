@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -107,7 +108,8 @@ struct annf_context {
     TensorPlan* tensor = nullptr;
     Profiler prof;
     // host-buffer entry
-    cudaStream_t host_stream = nullptr;
+    cudaStream_t host_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    cudaEvent_t ev_in[8] = {}, ev_comp[8] = {};
     float *h_coords = nullptr, *h_centers = nullptr, *h_forces = nullptr;
     double* h_energies = nullptr;
     size_t h_cap_coords = 0, h_cap_centers = 0, h_cap_energies = 0;
@@ -135,6 +137,12 @@ void release(annf_context* h) {
     cudaFree(h->h_coords); cudaFree(h->h_centers); cudaFree(h->h_forces); cudaFree(h->h_energies);
     if (h->staged_host) cudaFreeHost(h->staged_host);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->in_stream) cudaStreamDestroy(h->in_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
+    for (int i = 0; i < 8; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    }
     delete h;
 }
 
@@ -346,6 +354,12 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
         return fail(ANNF_ERR_UNSUPPORTED, "network too large for the fused batched kernel's shared memory in this precision");
     }
     ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+    ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        ANNF_CUDA_H(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        ANNF_CUDA_H(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+    }
     ANNF_CUDA_H(cudaDeviceSynchronize());
 #undef ANNF_CUDA_H
     *out = h;
@@ -467,18 +481,42 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
         ANNF_CUDA(cudaMalloc((void**) &h->h_energies, sizeof(double) * R));
         h->h_cap_energies = R;
     }
-    cudaStream_t s = h->host_stream;
-    ANNF_CUDA(cudaMemcpyAsync(h->h_coords, coords_host, sizeof(float) * n_coords, cudaMemcpyHostToDevice, s));
-    if (centers_host)
-        ANNF_CUDA(cudaMemcpyAsync(h->h_centers, centers_host, sizeof(float) * n_centers, cudaMemcpyHostToDevice, s));
-    // the kernels write the selected atoms only; everything else in forces_host comes back as zero
-    if (h->net.n_sel != atoms_per_replica) ANNF_CUDA(cudaMemsetAsync(h->h_forces, 0, sizeof(float) * n_coords, s));
-    annf_status st = annf_eval_batched(h, R, h->h_coords, atoms_per_replica, centers_host ? h->h_centers : nullptr,
-                                       h->h_forces, h->h_energies, s);
-    if (st != ANNF_OK) return st;
-    ANNF_CUDA(cudaMemcpyAsync(forces_host, h->h_forces, sizeof(float) * n_coords, cudaMemcpyDeviceToHost, s));
-    ANNF_CUDA(cudaMemcpyAsync(energies_host, h->h_energies, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
-    ANNF_CUDA(cudaStreamSynchronize(s));
+    // Software pipeline over replica chunks: the copy-in of chunk c+1 and the copy-out of chunk c-1 overlap
+    // the evaluation of chunk c (PCIe is full duplex; three streams ordered by events).
+    int chunks = 1;
+    {
+        const size_t bytes = sizeof(float) * n_coords;
+        if (bytes >= (4u << 20)) chunks = 4;
+        else if (bytes >= (1u << 20)) chunks = 2;
+        if (const char* env = getenv("ANNF_HOST_CHUNKS")) chunks = atoi(env);
+        chunks = std::max(1, std::min(std::min(chunks, 8), R));
+    }
+    const size_t row = (size_t) atoms_per_replica * 3;
+    const bool zero_fill = h->net.n_sel != atoms_per_replica;   // kernels write the selected atoms only
+    for (int c = 0; c < chunks; c++) {
+        const int r0 = (int) ((long long) R * c / chunks), r1 = (int) ((long long) R * (c + 1) / chunks), n = r1 - r0;
+        ANNF_CUDA(cudaMemcpyAsync(h->h_coords + r0 * row, coords_host + r0 * row, sizeof(float) * n * row, cudaMemcpyHostToDevice, h->in_stream));
+        if (centers_host)
+            ANNF_CUDA(cudaMemcpyAsync(h->h_centers + (size_t) r0 * h->net.num_center, centers_host + (size_t) r0 * h->net.num_center,
+                                      sizeof(float) * n * h->net.num_center, cudaMemcpyHostToDevice, h->in_stream));
+        ANNF_CUDA(cudaEventRecord(h->ev_in[c], h->in_stream));
+        ANNF_CUDA(cudaStreamWaitEvent(h->host_stream, h->ev_in[c], 0));
+        if (zero_fill) ANNF_CUDA(cudaMemsetAsync(h->h_forces + r0 * row, 0, sizeof(float) * n * row, h->host_stream));
+        annf_status st = annf_eval_batched(h, n, h->h_coords + r0 * row, atoms_per_replica,
+                                           centers_host ? h->h_centers + (size_t) r0 * h->net.num_center : nullptr,
+                                           h->h_forces + r0 * row, h->h_energies + r0, h->host_stream);
+        if (st != ANNF_OK) {
+            cudaStreamSynchronize(h->in_stream); cudaStreamSynchronize(h->host_stream); cudaStreamSynchronize(h->out_stream);
+            return st;
+        }
+        ANNF_CUDA(cudaEventRecord(h->ev_comp[c], h->host_stream));
+        ANNF_CUDA(cudaStreamWaitEvent(h->out_stream, h->ev_comp[c], 0));
+        ANNF_CUDA(cudaMemcpyAsync(forces_host + r0 * row, h->h_forces + r0 * row, sizeof(float) * n * row, cudaMemcpyDeviceToHost, h->out_stream));
+        ANNF_CUDA(cudaMemcpyAsync(energies_host + r0, h->h_energies + r0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->out_stream));
+    }
+    ANNF_CUDA(cudaStreamSynchronize(h->out_stream));
+    ANNF_CUDA(cudaStreamSynchronize(h->host_stream));
+    ANNF_CUDA(cudaStreamSynchronize(h->in_stream));
     return ANNF_OK;
 }
 

@@ -375,18 +375,39 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
 // SIMT companions
 // ------------------------------------------------------------------------------------------------
 // prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), centroid in fp64, write the TF32 pair.
+// One CTA per replica; the replica's selected coordinates are staged once in shared memory.
 __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
-                                                  float* __restrict__ x_hi, float* __restrict__ x_lo, int ld) {
+                                                  float* __restrict__ x_hi, float* __restrict__ x_lo, int ld, int contiguous) {
+    extern __shared__ float xs[];                           // [3 * A]
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int A = net.n_sel;
+    const int A = net.n_sel, n0 = 3 * A;
     const float* base = coords + (size_t) r * N * 3;
-    const double inv_scale = 1.0 / net.scale;
     __shared__ double red[8][3];
     __shared__ double com[3];
     double s[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < A; i += 256) {
-        const float* p = base + (size_t) net.sel_atoms[i] * 3;
-        s[0] += (double) __ldg(p); s[1] += (double) __ldg(p + 1); s[2] += (double) __ldg(p + 2);
+    if (contiguous) {
+        // selection is atoms 0..A-1 and rows are 16-byte aligned: straight vector copy, component = index % 3
+        const float4* src = reinterpret_cast<const float4*>(base);
+        for (int v = tid; v < n0 / 4; v += 256) {
+            const float4 p = __ldg(src + v);
+            *reinterpret_cast<float4*>(xs + 4 * v) = p;
+            const float e[4] = {p.x, p.y, p.z, p.w};
+            int c = (4 * v) % 3;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                s[0] += c == 0 ? (double) e[j] : 0.0;
+                s[1] += c == 1 ? (double) e[j] : 0.0;
+                s[2] += c == 2 ? (double) e[j] : 0.0;
+                c = c == 2 ? 0 : c + 1;
+            }
+        }
+    } else {
+        for (int i = tid; i < A; i += 256) {
+            const float* p = base + (size_t) net.sel_atoms[i] * 3;
+            const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+            xs[3 * i] = x; xs[3 * i + 1] = y; xs[3 * i + 2] = z;
+            s[0] += (double) x; s[1] += (double) y; s[2] += (double) z;
+        }
     }
     for (int c = 0; c < 3; c++) s[c] = warp_sum(s[c]);
     if (lane == 0) { red[warp][0] = s[0]; red[warp][1] = s[1]; red[warp][2] = s[2]; }
@@ -394,59 +415,82 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     if (tid < 3) {
         double t = 0.0;
         for (int w = 0; w < 8; w++) t += red[w][tid];
-        com[tid] = t / A;                                   // centroid of the unscaled coordinates
+        com[tid] = t / A;                                    // centroid of the unscaled coordinates
     }
     __syncthreads();
-    for (int i = tid; i < 3 * A; i += 256) {
-        const int atom = i / 3, c = i - 3 * atom;
-        const double v = ((double) __ldg(base + (size_t) net.sel_atoms[atom] * 3 + c) - com[c]) * inv_scale;
-        float hi, lo;
-        split_tf32((float) v, hi, lo);
-        x_hi[(size_t) r * ld + i] = hi;
-        x_lo[(size_t) r * ld + i] = lo;
+    const double inv_scale = 1.0 / net.scale;
+    const double c0 = com[0], c1 = com[1], c2 = com[2];
+    float* oh = x_hi + (size_t) r * ld;
+    float* ol = x_lo + (size_t) r * ld;
+    // centring in fp64: a molecule far from the origin must not lose bits of (p - centroid)
+    for (int v = tid; v < n0 / 4; v += 256) {
+        const float4 p = *reinterpret_cast<const float4*>(xs + 4 * v);
+        const float e[4] = {p.x, p.y, p.z, p.w};
+        float hi[4], lo[4];
+        int c = (4 * v) % 3;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
+            split_tf32((float) (((double) e[j] - cc) * inv_scale), hi[j], lo[j]);
+            c = c == 2 ? 0 : c + 1;
+        }
+        *reinterpret_cast<float4*>(oh + 4 * v) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(ol + 4 * v) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
 // head: output layer forward (fp64 accumulate), umbrella energy + gradient (output_head), and the
 // backward contraction through the output connection, fused with act'() of the last hidden layer.
-// The output-connection weights sit in shared memory; one warp per replica, kHeadReplicas per CTA.
-constexpr int kHeadReplicas = 8;
-__global__ void __launch_bounds__(256) head_kernel(NetView net, int R, const float* __restrict__ centers,
-                                                  const float* __restrict__ a_hi, const float* __restrict__ a_lo, int ld,
-                                                  float* __restrict__ d_hi, float* __restrict__ d_lo, double* __restrict__ energies) {
-    extern __shared__ double w_s[];                         // [nL][nH]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One 128-thread CTA per replica: every thread owns hidden units tid, tid+128, ... so the dependent
+// chains are short; the nL output sums are reduced with shuffles + one shared-memory hop.
+constexpr int kHeadThreads = 128;
+constexpr int kHeadMaxOut = 64;
+__global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, const float* __restrict__ centers,
+                                                           const float* __restrict__ a_hi, const float* __restrict__ a_lo, int ld,
+                                                           float* __restrict__ d_hi, float* __restrict__ d_lo, double* __restrict__ energies) {
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = net.L, nH = net.nodes[L - 2], nL = net.nodes[L - 1];
-    __shared__ double zs[kHeadReplicas][64], dzs[kHeadReplicas][64], cen[kHeadReplicas][64];
-    const double* W = net.W64 + net.w_off[L - 2];
+    __shared__ double part[4][kHeadMaxOut];
+    __shared__ double zs[kHeadMaxOut], dzs[kHeadMaxOut], cen[kHeadMaxOut];
+    __shared__ float dzf[kHeadMaxOut];
+    const double* W = net.W64 + net.w_off[L - 2];           // [nL][nH]
+    const float* W32 = net.W32 + net.w_off[L - 2];
     const double* b = net.b64 + net.b_off[L - 2];
-    for (int i = threadIdx.x; i < nL * nH; i += 256) w_s[i] = __ldg(W + i);
-    __syncthreads();
-    const int r = blockIdx.x * kHeadReplicas + warp;
-    if (r >= R) return;
     const float* ah = a_hi + (size_t) r * ld;
     const float* al = a_lo + (size_t) r * ld;
-    for (int j = 0; j < nL; j++) {
-        double acc = 0.0;
-        for (int m = lane; m < nH; m += 32) acc = fma(w_s[j * nH + m], (double) ah[m] + (double) al[m], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) zs[warp][j] = acc + b[j];
+    for (int j0 = 0; j0 < nL; j0 += 8) {                    // 8 outputs at a time: 8 independent accumulators per thread
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int m = tid; m < nH; m += kHeadThreads) {
+            const double a = (double) (__ldg(ah + m) + __ldg(al + m));   // hi + lo is exact in fp32
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (j0 + u < nL) acc[u] = fma(__ldg(W + (size_t) (j0 + u) * nH + m), a, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double s = warp_sum(acc[u]);
+            if (lane == 0 && j0 + u < nL) part[warp][j0 + u] = s;
+        }
     }
-    for (int c = lane; c < net.num_center; c += 32)
-        cen[warp][c] = centers ? (double) centers[(size_t) r * net.num_center + c] : net.center[c];
-    __syncwarp();
-    if (lane == 0) energies[r] = output_head(net.types[L - 2], nL, zs[warp], 1, cen[warp], *net.k_dev, dzs[warp], 1);
-    __syncwarp();
+    for (int c = tid; c < net.num_center; c += kHeadThreads)
+        cen[c] = centers ? (double) centers[(size_t) r * net.num_center + c] : net.center[c];
+    __syncthreads();
+    if (tid < nL) zs[tid] = ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + b[tid];
+    __syncthreads();
+    if (tid == 0) energies[r] = output_head(net.types[L - 2], nL, zs, 1, cen, *net.k_dev, dzs, 1);
+    __syncthreads();
+    if (tid < nL) dzf[tid] = (float) dzs[tid];
+    __syncthreads();
     const int hidden_type = net.types[L - 3];
-    for (int m = lane; m < nH; m += 32) {
-        double acc = 0.0;
-        for (int j = 0; j < nL; j++) acc = fma(w_s[j * nH + m], dzs[warp][j], acc);
+    for (int m = tid; m < nH; m += kHeadThreads) {          // the result is re-split to TF32 pairs: fp32 FMA is enough here
+        float acc = 0.f;
+        for (int j = 0; j < nL; j++) acc = fmaf(__ldg(W32 + (size_t) j * nH + m), dzf[j], acc);
         if (hidden_type == ANNF_TANH) {
-            const double a = (double) ah[m] + (double) al[m];
-            acc *= (1.0 - a * a);
+            const float a = __ldg(ah + m) + __ldg(al + m);
+            acc *= (1.f - a * a);
         }
         float hi, lo;
-        split_tf32((float) acc, hi, lo);
+        split_tf32(acc, hi, lo);
         d_hi[(size_t) r * ld + m] = hi;
         d_lo[(size_t) r * ld + m] = lo;
     }
@@ -455,22 +499,28 @@ __global__ void __launch_bounds__(256) head_kernel(NetView net, int R, const flo
 // colmean: mean over atoms of the input gradient, per replica and component, WITHOUT forming the gradient:
 //   (1/A) sum_i g[3i+c] = (1/A) sum_k D1[k] * (sum_i W0[k][3i+c])     (wsum precomputed at plan creation)
 // This is the Jacobian term of centroid removal (ANN_ReferenceKernels.cpp:402-406); knowing it before the last
-// backward contraction lets that GEMM's epilogue write the forces directly.  One warp per replica.
-__global__ void __launch_bounds__(256) colmean_kernel(int R, int K, int A, const float* __restrict__ d_hi,
+// backward contraction lets that GEMM's epilogue write the forces directly.  One 128-thread CTA per replica.
+__global__ void __launch_bounds__(128) colmean_kernel(int R, int K, int A, const float* __restrict__ d_hi,
                                                      const float* __restrict__ d_lo, int ld, const double* __restrict__ wsum,
                                                      float* __restrict__ row_mean) {
-    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= R) return;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double part[4][3];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int k = lane; k < K; k += 32) {
-        const double d = (double) d_hi[(size_t) r * ld + k] + (double) d_lo[(size_t) r * ld + k];
+    for (int k = tid; k < K; k += 128) {
+        const double d = (double) (__ldg(d_hi + (size_t) r * ld + k) + __ldg(d_lo + (size_t) r * ld + k));
         s0 = fma(d, __ldg(wsum + k), s0);
         s1 = fma(d, __ldg(wsum + K + k), s1);
         s2 = fma(d, __ldg(wsum + 2 * K + k), s2);
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0)
-        *reinterpret_cast<float4*>(row_mean + (size_t) r * 4) = make_float4((float) (s0 / A), (float) (s1 / A), (float) (s2 / A), 0.f);
+    if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+        const double t0 = (part[0][0] + part[1][0]) + (part[2][0] + part[3][0]);
+        const double t1 = (part[0][1] + part[1][1]) + (part[2][1] + part[3][1]);
+        const double t2 = (part[0][2] + part[1][2]) + (part[2][2] + part[3][2]);
+        *reinterpret_cast<float4*>(row_mean + (size_t) r * 4) = make_float4((float) (t0 / A), (float) (t1 / A), (float) (t2 / A), 0.f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -589,10 +639,9 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     for (int l = 1; l + 1 < L; l++)
         if (net.nodes[l] < 64) return no("hidden layers narrower than 64 nodes are not a dense contraction worth the tensor pipe");
     if (!encode_fn()) return no("cuTensorMapEncodeTiled is not available from this driver");
-    if ((size_t) net.nodes[L - 1] * net.nodes[L - 2] * sizeof(double) > 160 * 1024)
-        return no("output connection too large for the head kernel's shared memory");
-    if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-        return no("cannot configure the head kernel");
+    if ((size_t) net.nodes[0] * sizeof(float) > 200 * 1024) return no("input layer too wide for the prep kernel's shared memory");
+    if (cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return no("cannot configure the prep kernel");
     TensorPlan* t = new TensorPlan();
     t->L = L;
     int dev = 0;
@@ -760,7 +809,9 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
         return e;
     };
     err = timed("prep_kernel", [&] {
-        prep_kernel<<<R, 256, 0, stream>>>(net, R, coords, atoms_per_replica, t->x_hi[0], t->x_lo[0], t->ld[0]);
+        const int contiguous = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0;
+        prep_kernel<<<R, 256, sizeof(float) * t->nodes[0], stream>>>(net, R, coords, atoms_per_replica, t->x_hi[0], t->x_lo[0],
+                                                                     t->ld[0], contiguous);
         return cudaGetLastError();
     });
     if (err != cudaSuccess) return err;
@@ -770,17 +821,15 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
         if (err != cudaSuccess) return err;
     }
     err = timed("head_kernel", [&] {
-        const size_t smem = sizeof(double) * (size_t) t->nodes[L - 1] * t->nodes[L - 2];
-        head_kernel<<<(R + kHeadReplicas - 1) / kHeadReplicas, 256, smem, stream>>>(
-            net, R, centers, t->x_hi[L - 2], t->x_lo[L - 2], t->ld[L - 2], t->d_hi[L - 2], t->d_lo[L - 2], energies);
+        head_kernel<<<R, kHeadThreads, 0, stream>>>(net, R, centers, t->x_hi[L - 2], t->x_lo[L - 2], t->ld[L - 2],
+                                                    t->d_hi[L - 2], t->d_lo[L - 2], energies);
         return cudaGetLastError();
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : t->bwd) {
         if (op.p.epi == EPI_FORCE) {
             err = timed("colmean_kernel", [&] {
-                colmean_kernel<<<(R + 7) / 8, 256, 0, stream>>>(R, t->nodes[1], net.n_sel, t->d_hi[1], t->d_lo[1], t->ld[1],
-                                                                 t->wsum, t->row_mean);
+                colmean_kernel<<<R, 128, 0, stream>>>(R, t->nodes[1], net.n_sel, t->d_hi[1], t->d_lo[1], t->ld[1], t->wsum, t->row_mean);
                 return cudaGetLastError();
             });
             if (err != cudaSuccess) return err;

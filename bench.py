@@ -254,8 +254,6 @@ def main():
 
     sampler = ClockSampler(local_rank)
     launches0 = kernel.info()["kernel_launches"]
-    kernel.set_profiling(True)
-    kernel.kernel_times(reset=True)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     if rotate or single:
@@ -289,9 +287,20 @@ def main():
         gpu_ms = float(sum(a.elapsed_time(b) for a, b in evs))
         l2_policy = "L2 flushed (252 MB write) between steps; each step timed with its own CUDA event pair"
     sampler.stop()
+    launches = kernel.info()["kernel_launches"] - launches0
+
+    # second pass over the same steps with a CUDA-event pair around every kernel launch (on the launching stream):
+    # per-kernel durations for the roofline.  Kept out of the headline region because each event pair costs ~4 us.
+    kernel.set_profiling(True)
+    kernel.kernel_times(reset=True)
+    prof_steps = min(steps, 200)
+    for i in range(prof_steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        step(i)
+    torch.cuda.synchronize()
     kernel.set_profiling(False)
     times = kernel.kernel_times(reset=True)
-    launches = kernel.info()["kernel_launches"] - launches0
 
     t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
     if world > 1:
