@@ -13,10 +13,13 @@
 // the centring Jacobian is one mean per component, computed ahead of the last backward contraction
 // ("colmean"), whose epilogue then writes the forces directly.
 //
-// GEMM kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0  : TMA producer   - cp.async.bulk.tensor.2d of A_hi, A_lo, B_hi, B_lo (128B swizzle) per stage
-//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
-//   warps 2-5: epilogue      - tcgen05.ld TMEM -> registers -> bias / tanh / tanh' -> hi/lo stores
+// GEMM kernel anatomy (one 128 x BN output tile per CTA, BN = 128 or 256):
+//   epilogue warps (BN/32 of them, first): tcgen05.ld TMEM -> registers -> bias / tanh / tanh' -> hi/lo or force stores
+//   producer warp : TMA - cp.async.bulk.tensor.2d of A_hi, A_lo, B_hi, B_lo (128B swizzle) per stage
+//   MMA warp      : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+// (BN = 256: setmaxnreg moves registers from the producer/MMA warpgroup to the eight epilogue warps.)
+// Every kernel of the step is launched with programmatic dependent launch: its prologue (barrier init,
+// TMEM allocation, descriptor prefetch) overlaps the tail of the kernel before it.
 // Accumulation: the tensor core's fp32 accumulator does not round to nearest, so a K = 4500 chain in
 // TMEM costs ~30x the error of the products themselves (measured).  The K loop is therefore cut into
 // chunks of kChunk K-blocks: a chunk accumulates in one of two TMEM buffers while the epilogue warps
@@ -29,8 +32,10 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "annf_common.cuh"
@@ -43,7 +48,6 @@ namespace annf {
 constexpr int BM = 128;               // replicas per tile = UMMA M
 constexpr int BK = 32;                // fp32 elements per K-block = 128 bytes = one swizzle span
 constexpr int UMMA_K = 8;             // tf32: 32 bytes per instruction along K
-constexpr int kGemmThreads = 192;
 
 constexpr int kChunk = 2;             // K-blocks accumulated in TMEM between promotions (K = 64: 24 chained MMAs)
 
@@ -143,13 +147,18 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 }
 
 template <int BN> struct GemmCfg {
+    static constexpr int kEpiWarps = BN / 32;                                   // each owns 32 TMEM lanes x 128 columns
+    static constexpr int kThreads = (kEpiWarps + 4) * 32;                       // + producer warp, MMA warp, 2 idle (warpgroup padding)
     static constexpr int kStageBytes = (2 * BM + 2 * BN) * BK * 4;
-    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int kStages = BN >= 256 ? 2 : 3;
     static constexpr int kStagingLd = BN + 4;                                   // fp32 elements, padded against bank conflicts
     static constexpr int kStagingBytes = BM * kStagingLd * 4;
     static constexpr int kDataBytes = kStageBytes * kStages > kStagingBytes ? kStageBytes * kStages : kStagingBytes;
     static constexpr int kSmemBytes = kDataBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One epilogue element group: 4 consecutive columns of one output row.
 __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int n, float4 v) {
@@ -199,11 +208,13 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
 }
 
 template <int BN, int S>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
+    constexpr int kEpiWarps = Cfg::kEpiWarps;
+    constexpr int kColsPerWarp = 128;                       // accumulator columns held in registers by one epilogue thread
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms (TMA and UMMA must agree on address bits 7..9)
     unsigned char* data = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -223,7 +234,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const int num_kb = kb1 - kb0;
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
 
-    if (warp == 0 && lane == 0) {
+    pdl_launch_dependents();                                // the next kernel may start its own prologue now
+    if (warp == kEpiWarps && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
         for (int s = 0; s < kStages; s++) {
             mbar_init(smem_u32(&bar_full[s]), 1);
@@ -231,11 +243,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(smem_u32(&bar_acc_full[b]), 1);
-            mbar_init(smem_u32(&bar_acc_empty[b]), 4);            // one arrival per epilogue warp
+            mbar_init(smem_u32(&bar_acc_empty[b]), kEpiWarps);    // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kEpiWarps + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -243,76 +255,86 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                             // everything below reads what earlier kernels wrote
 
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int i = 0; i < num_kb; i++) {
-                const int s = i % kStages;
-                const uint32_t ph = (uint32_t) (i / kStages) & 1u;
-                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                      // slot free
-                const uint32_t full = smem_u32(&bar_full[s]);
-                mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
-                const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
-                const int kc = (kb0 + i) * BK;
-                tma_load_2d(base, &tm_a_hi, full, kc, m0);
-                tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
-                tma_load_2d(base + 2 * BM * BK * 4, &tm_b_hi, full, kc, n0);
-                tma_load_2d(base + 2 * BM * BK * 4 + BN * BK * 4, &tm_b_lo, full, kc, n0);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread).  Chunk c accumulates into TMEM buffer c & 1. =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BN);
-            int i = 0;
-            for (int c = 0; c < num_chunks; c++) {
-                const int buf = c & 1;
-                const uint32_t use = (uint32_t) (c >> 1);
-                mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);        // epilogue drained this buffer
-                tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * BN);
-                const int i_end = min(num_kb, (c + 1) * kChunk);
-                bool first = true;
-                for (; i < i_end; i++) {
+    if (warp >= kEpiWarps) {
+        // ===== producer / MMA warpgroup: needs few registers =====
+        if (BN >= 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+        if (warp == kEpiWarps) {
+            // ----- TMA producer -----
+            if (lane == 0) {
+                for (int i = 0; i < num_kb; i++) {
                     const int s = i % kStages;
                     const uint32_t ph = (uint32_t) (i / kStages) & 1u;
-                    mbar_wait(smem_u32(&bar_full[s]), ph);                         // TMA bytes landed
-                    tcgen05_fence_after();
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
                     const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
-                    const uint32_t a_hi = base, a_lo = base + BM * BK * 4;
-                    const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + BN * BK * 4;
+                    const int kc = (kb0 + i) * BK;
+                    tma_load_2d(base, &tm_a_hi, full, kc, m0);
+                    tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
 #pragma unroll
-                    for (int kk = 0; kk < BK / UMMA_K; kk++) {
-                        const uint32_t off = kk * UMMA_K * 4;                      // 32 bytes along K inside the swizzle span
-                        const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
-                        const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
-                        umma_tf32(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);     // small terms first
-                        umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
-                        first = false;
+                    for (int h = 0; h < BN / 128; h++) {                          // TMA boxes are at most 256 rows; use 128-row boxes
+                        tma_load_2d(base + 2 * BM * BK * 4 + h * 128 * BK * 4, &tm_b_hi, full, kc, n0 + h * 128);
+                        tma_load_2d(base + 2 * BM * BK * 4 + BN * BK * 4 + h * 128 * BK * 4, &tm_b_lo, full, kc, n0 + h * 128);
                     }
-                    umma_commit(smem_u32(&bar_empty[s]));                          // frees the slot when these MMAs retire
                 }
-                umma_commit(smem_u32(&bar_acc_full[buf]));                         // chunk complete
+            }
+        } else if (warp == kEpiWarps + 1) {
+            // ----- MMA issuer (one thread).  Chunk c accumulates into TMEM buffer c & 1. -----
+            if (lane == 0) {
+                constexpr uint32_t idesc = umma_idesc_tf32(BN);
+                int i = 0;
+                for (int c = 0; c < num_chunks; c++) {
+                    const int buf = c & 1;
+                    const uint32_t use = (uint32_t) (c >> 1);
+                    mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);    // epilogue drained this buffer
+                    tcgen05_fence_after();
+                    const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * BN);
+                    const int i_end = min(num_kb, (c + 1) * kChunk);
+                    bool first = true;
+                    for (; i < i_end; i++) {
+                        const int s = i % kStages;
+                        const uint32_t ph = (uint32_t) (i / kStages) & 1u;
+                        mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed
+                        tcgen05_fence_after();
+                        const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
+                        const uint32_t a_hi = base, a_lo = base + BM * BK * 4;
+                        const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + BN * BK * 4;
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                            const uint32_t off = kk * UMMA_K * 4;                  // 32 bytes along K inside the swizzle span
+                            const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
+                            const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
+                            umma_tf32(tmem_acc, dal, dbh, idesc, first ? 0u : 1u); // small terms first
+                            umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+                            umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                            first = false;
+                        }
+                        umma_commit(smem_u32(&bar_empty[s]));                      // frees the slot when these MMAs retire
+                    }
+                    umma_commit(smem_u32(&bar_acc_full[buf]));                     // chunk complete
+                }
             }
         }
     } else {
         // ===== epilogue warps: promote TMEM chunks into fp32 registers (round-to-nearest adds) =====
+        if (BN >= 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         const int q = warp & 3;                                                    // TMEM lane quarter this warp may read
+        const int col0 = (warp >> 2) * kColsPerWarp;                               // column range of this warp
         const int row = q * 32 + lane;
-        float acc[BN];
+        float acc[kColsPerWarp];
 #pragma unroll
-        for (int j = 0; j < BN; j++) acc[j] = 0.f;
+        for (int j = 0; j < kColsPerWarp; j++) acc[j] = 0.f;
         for (int c = 0; c < num_chunks; c++) {
             const int buf = c & 1;
             const uint32_t use = (uint32_t) (c >> 1);
             mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
             tcgen05_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < BN / 32; cc++) {
+            for (int cc = 0; cc < kColsPerWarp / 32; cc++) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (buf * BN + cc * 32), r);
+                tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (buf * BN + col0 + cc * 32), r);
 #pragma unroll
                 for (int j = 0; j < 32; j++) acc[cc * 32 + j] += __uint_as_float(r[j]);
             }
@@ -324,16 +346,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             const int m = m0 + row;
             if (m < p.M) {
 #pragma unroll
-                for (int j = 0; j < BN; j += 4) {
-                    const int n = n0 + j;
+                for (int j = 0; j < kColsPerWarp; j += 4) {
+                    const int n = n0 + col0 + j;
                     if (n < p.N) epilogue_store4(p, m, n, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
                 }
             }
         } else {
             // park the partial tile (all TMA loads have landed and been consumed: the stage buffers are free)
-            float* dst = reinterpret_cast<float*>(data) + (size_t) row * Cfg::kStagingLd;
+            float* dst = reinterpret_cast<float*>(data) + (size_t) row * Cfg::kStagingLd + col0;
 #pragma unroll
-            for (int j = 0; j < BN; j += 4)
+            for (int j = 0; j < kColsPerWarp; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
     }
@@ -341,15 +363,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     if (S > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();                                                            // every partial tile is parked
-        if (warp >= 2) {
+        if (warp < kEpiWarps) {
             constexpr int kRows = BM / S;                                          // rows this CTA reduces
             constexpr int kVecPerRow = BN / 4;
-            const int t = threadIdx.x - 64;                                        // 0..127
+            const int t = threadIdx.x;                                             // 0 .. 32 * kEpiWarps - 1
             float* staging = reinterpret_cast<float*>(data);
             const float* peer[S];
 #pragma unroll
             for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, r);
-            for (int v = t; v < kRows * kVecPerRow; v += 128) {
+            for (int v = t; v < kRows * kVecPerRow; v += 32 * kEpiWarps) {
                 const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -365,7 +387,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     } else {
         __syncthreads();
     }
-    if (warp == 1) {
+    if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
     }
@@ -379,6 +401,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
 __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
                                                   float* __restrict__ x_hi, float* __restrict__ x_lo, int ld, int contiguous) {
     extern __shared__ float xs[];                           // [3 * A]
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = net.n_sel, n0 = 3 * A;
     const float* base = coords + (size_t) r * N * 3;
@@ -448,6 +472,8 @@ constexpr int kHeadMaxOut = 64;
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, const float* __restrict__ centers,
                                                            const float* __restrict__ a_hi, const float* __restrict__ a_lo, int ld,
                                                            float* __restrict__ d_hi, float* __restrict__ d_lo, double* __restrict__ energies) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = net.L, nH = net.nodes[L - 2], nL = net.nodes[L - 1];
     __shared__ double part[4][kHeadMaxOut];
@@ -503,6 +529,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
 __global__ void __launch_bounds__(128) colmean_kernel(int R, int K, int A, const float* __restrict__ d_hi,
                                                      const float* __restrict__ d_lo, int ld, const double* __restrict__ wsum,
                                                      float* __restrict__ row_mean) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double part[4][3];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -560,7 +588,6 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 struct GemmOp {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     GemmParams p;
-    int bn;
     char name[48];
 };
 
@@ -577,6 +604,7 @@ struct TensorPlan {
     float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {}, *row_mean = nullptr;
     double* wsum = nullptr;                         // [3][n_1]: sum over atoms of W_0[k][3i+c]
     bool sel_identity = false;                      // selection is atoms 0..A-1 in order
+    int force_bn = 0;                               // ANNF_GEMM_BN=128|256 overrides the tile-width heuristic (experiments)
     std::vector<GemmOp> fwd, bwd;
 };
 
@@ -644,6 +672,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
         return no("cannot configure the prep kernel");
     TensorPlan* t = new TensorPlan();
     t->L = L;
+    if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -707,10 +736,9 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
     for (int l = 0; l + 2 < L; l++) {                 // forward: X_{l+1} = act(X_l W_l^T + b)
         GemmOp op;
         memset(&op, 0, sizeof(op));
-        op.bn = 128;
         const int K = t->nodes[l], N = t->nodes[l + 1];
         bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, t->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, t->ld[l], BM) &&
-                  make_map(&op.b_hi, t->w_hi[l], N, K, t->ld[l], op.bn) && make_map(&op.b_lo, t->w_lo[l], N, K, t->ld[l], op.bn);
+                  make_map(&op.b_hi, t->w_hi[l], N, K, t->ld[l], 128) && make_map(&op.b_lo, t->w_lo[l], N, K, t->ld[l], 128);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
         op.p.epi = t->types[l] == ANNF_TANH ? EPI_BIAS_TANH : EPI_BIAS_LINEAR;
@@ -722,10 +750,9 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
     for (int l = L - 3; l >= 0; l--) {                // backward: D_l = (D_{l+1} W_l) (.) act'(X_l);  l = 0 -> G0
         GemmOp op;
         memset(&op, 0, sizeof(op));
-        op.bn = 128;
         const int K = t->nodes[l + 1], N = t->nodes[l];
         bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, t->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, t->ld[l + 1], BM) &&
-                  make_map(&op.b_hi, t->wt_hi[l], N, K, t->ld[l + 1], op.bn) && make_map(&op.b_lo, t->wt_lo[l], N, K, t->ld[l + 1], op.bn);
+                  make_map(&op.b_hi, t->wt_hi[l], N, K, t->ld[l + 1], 128) && make_map(&op.b_lo, t->wt_lo[l], N, K, t->ld[l + 1], 128);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
         if (l == 0) {
@@ -743,6 +770,32 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
     return cudaSuccess;
 }
 
+// Launch with programmatic dependent launch allowed (and, for the GEMM, its split-K cluster shape).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_z,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+    if (cluster_z > 0) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = cluster_z;
+        n++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <int BN, int S>
 static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStream_t stream) {
     static bool configured[64] = {};
@@ -753,19 +806,8 @@ static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStre
         if (err != cudaSuccess) return err;
         configured[dev] = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, S);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = GemmCfg<BN>::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = S;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm3x_kernel<BN, S>, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p);
+    return launch_pdl(gemm3x_kernel<BN, S>, dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, S), dim3(GemmCfg<BN>::kThreads),
+                      GemmCfg<BN>::kSmemBytes, stream, S, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p);
 }
 
 static int pick_split(int tiles, int k_blocks, int sm_count) {
@@ -784,8 +826,23 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         const bool vec_ok = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(forces) & 15) == 0;
         p.sel_atoms = vec_ok ? nullptr : net.sel_atoms;
     }
-    const int tiles = ((p.N + 127) / 128) * ((R + BM - 1) / BM);
+    // 256-wide tiles move 25% fewer operand bytes per flop and halve the CTA count (one wave instead of two for
+    // the 4500-wide backward GEMM: 59.8 -> 48.2 us measured), but their 2-stage pipeline and 8-way split-K reduce
+    // lose on GEMMs that need split-K to fill the machine (fwd 1024x512x4500: 41 -> 74 us).  So: 256 only when the
+    // 128-wide tiling would already fill the SMs without splitting K.
+    const int tiles128 = ((p.N + 127) / 128) * ((R + BM - 1) / BM);
+    int bn = tiles128 > t->sm_count ? 256 : 128;
+    if (t->force_bn == 128 || t->force_bn == 256) bn = t->force_bn;
+    const int tiles = ((p.N + bn - 1) / bn) * ((R + BM - 1) / BM);
     const int s = pick_split(tiles, (p.K + BK - 1) / BK, t->sm_count);
+    if (bn == 256) {
+        switch (s) {
+        case 8: return launch_gemm_t<256, 8>(op, p, stream);
+        case 4: return launch_gemm_t<256, 4>(op, p, stream);
+        case 2: return launch_gemm_t<256, 2>(op, p, stream);
+        default: return launch_gemm_t<256, 1>(op, p, stream);
+        }
+    }
     switch (s) {
     case 8: return launch_gemm_t<128, 8>(op, p, stream);
     case 4: return launch_gemm_t<128, 4>(op, p, stream);
@@ -810,9 +867,8 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
     };
     err = timed("prep_kernel", [&] {
         const int contiguous = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0;
-        prep_kernel<<<R, 256, sizeof(float) * t->nodes[0], stream>>>(net, R, coords, atoms_per_replica, t->x_hi[0], t->x_lo[0],
-                                                                     t->ld[0], contiguous);
-        return cudaGetLastError();
+        return launch_pdl(prep_kernel, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 0, net, R, coords, atoms_per_replica,
+                          t->x_hi[0], t->x_lo[0], t->ld[0], contiguous);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : t->fwd) {
@@ -821,16 +877,15 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
         if (err != cudaSuccess) return err;
     }
     err = timed("head_kernel", [&] {
-        head_kernel<<<R, kHeadThreads, 0, stream>>>(net, R, centers, t->x_hi[L - 2], t->x_lo[L - 2], t->ld[L - 2],
-                                                    t->d_hi[L - 2], t->d_lo[L - 2], energies);
-        return cudaGetLastError();
+        return launch_pdl(head_kernel, dim3(R), dim3(kHeadThreads), 0, stream, 0, net, R, centers, (const float*) t->x_hi[L - 2],
+                          (const float*) t->x_lo[L - 2], t->ld[L - 2], t->d_hi[L - 2], t->d_lo[L - 2], energies);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : t->bwd) {
         if (op.p.epi == EPI_FORCE) {
             err = timed("colmean_kernel", [&] {
-                colmean_kernel<<<R, 128, 0, stream>>>(R, t->nodes[1], net.n_sel, t->d_hi[1], t->d_lo[1], t->ld[1], t->wsum, t->row_mean);
-                return cudaGetLastError();
+                return launch_pdl(colmean_kernel, dim3(R), dim3(128), 0, stream, 0, R, t->nodes[1], net.n_sel, (const float*) t->d_hi[1],
+                                  (const float*) t->d_lo[1], t->ld[1], (const double*) t->wsum, t->row_mean);
             });
             if (err != cudaSuccess) return err;
         }

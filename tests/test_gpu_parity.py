@@ -279,6 +279,20 @@ def test_tensor_core_path_matches_oracle(nodes, types, R):
     np.testing.assert_array_equal(f, f2)
 
 
+@pytest.mark.parametrize("bn", ["128", "256"])
+def test_tensor_core_tile_widths_agree(bn, monkeypatch):
+    """Both GEMM tile widths (128: 4 epilogue warps; 256: 8 epilogue warps + setmaxnreg) against the oracle,
+    with split-K 4 and 8, ragged N (600 = 2*256 + 88) and ragged K."""
+    monkeypatch.setenv("ANNF_GEMM_BN", bn)
+    nodes, types, R = [1200, 600, 320, 6], ["Tanh", "Tanh", "Tanh"], 150
+    force = synthetic.make_force(nodes, types, 400, seed=51)
+    pos = synthetic.make_positions(400, R, seed=52)
+    e, f, kernel = run_batched(force, pos, None, precision="tf32x3")
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=2e-5)
+    assert max_norm_rel(f, f_ref) <= F_RTOL
+
+
 def test_tensor_core_path_rejects_what_it_cannot_do():
     force = synthetic.make_force([21, 40, 4], ["Tanh", "Circular"], 7, seed=1)
     with pytest.raises(_capi.ANNForceError):
