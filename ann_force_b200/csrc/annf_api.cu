@@ -17,7 +17,7 @@
 
 namespace annf {
 // annf_single.cu
-size_t single_smem_bytes(const NetView& net);
+size_t single_smem_bytes(const NetView& net, int cluster_size);
 cudaError_t prepare_single(const NetView& net, int cluster_size);
 cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq, const void* posq_corr,
                           unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream);
@@ -305,10 +305,10 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     int cl = 1;
     while (cl < 8 && weight_bytes / cl > 48.0 * 1024) cl *= 2;
     h->cluster_size = cl;
-    if (single_smem_bytes(net) > 226 * 1024) {
+    if (single_smem_bytes(net, cl) > 226 * 1024) {
         release(h);
         return fail(ANNF_ERR_UNSUPPORTED, "network too large for the single-replica kernel's shared memory (%zu bytes)",
-                    single_smem_bytes(net));
+                    single_smem_bytes(net, cl));
     }
     ANNF_CUDA_H(prepare_single(net, cl));
 

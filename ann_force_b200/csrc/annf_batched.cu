@@ -32,6 +32,9 @@ struct BatchedArgs {
     double* energies;
     int x_off[kMaxLayers];     // per hidden layer: offset (in T elements / TR) of its 2*n extra slots, or -1
     int extra_nodes;           // total extra slot rows
+    int ws_off[kMaxLayers];    // shared-memory weight staging: element offset of connection l ...
+    int ws_ld[kMaxLayers];     // ... and its (odd) row stride; rows are [n_out][ws_ld]
+    int ws_total;              // staged elements in total, 0 = weights stay in global memory
 };
 
 template <typename T, int TR>
@@ -48,11 +51,40 @@ __device__ __forceinline__ void load_row(const T* p, T (&x)[TR]) {
     }
 }
 
-// out[j][r] = sum_i Wg[i * n_lane + j] * in[i][r]   for j < n_lane, r < TR; epilogue(j, acc) consumes it.
+// acc[r] += sum_{i in [i0,i1)} w(i, j) * in[i][r]   with w(i, j) = Wp[i * s_loop + j * s_lane].
+// Weight loads are issued eight at a time ahead of their use: the loop is latency-bound on them otherwise.
+template <typename T, typename ACC, int TR>
+__device__ __forceinline__ void accumulate_range(const T* __restrict__ Wp, size_t s_loop, size_t s_lane, int j, bool active,
+                                                 int i0, int i1, const T* in, ACC (&acc)[TR]) {
+    constexpr int U = 8;
+    const T* wj = Wp + (size_t) j * s_lane;
+    int i = i0;
+    for (; i + U <= i1; i += U) {
+        T w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = active ? wj[(size_t) (i + u) * s_loop] : T(0);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            T x[TR];
+            load_row<T, TR>(in + (size_t) (i + u) * TR, x);
+#pragma unroll
+            for (int r = 0; r < TR; r++) acc[r] = fma((ACC) w[u], (ACC) x[r], acc[r]);
+        }
+    }
+    for (; i < i1; i++) {
+        const T w = active ? wj[(size_t) i * s_loop] : T(0);
+        T x[TR];
+        load_row<T, TR>(in + (size_t) i * TR, x);
+#pragma unroll
+        for (int r = 0; r < TR; r++) acc[r] = fma((ACC) w, (ACC) x[r], acc[r]);
+    }
+}
+
+// out[j][r] = sum_i w(i, j) * in[i][r]   for j < n_lane, r < TR; epilogue(j, acc) consumes it.
 // Must be called by all threads of the CTA (contains __syncthreads when the loop dimension is split).
 template <typename T, typename ACC, int TR, typename Epilogue>
-__device__ __forceinline__ void dense_tile(const T* __restrict__ Wg, int n_lane, int n_loop, const T* in,
-                                           ACC* scratch, Epilogue epilogue) {
+__device__ __forceinline__ void dense_tile(const T* __restrict__ Wp, size_t s_loop, size_t s_lane, int n_lane, int n_loop,
+                                           const T* in, ACC* scratch, Epilogue epilogue) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (n_lane + 31) >> 5;
     if (nchunks >= kBatchWarps) {
@@ -62,14 +94,7 @@ __device__ __forceinline__ void dense_tile(const T* __restrict__ Wg, int n_lane,
             ACC acc[TR];
 #pragma unroll
             for (int r = 0; r < TR; r++) acc[r] = ACC(0);
-#pragma unroll 4
-            for (int i = 0; i < n_loop; i++) {
-                const T w = active ? __ldg(Wg + (size_t) i * n_lane + j) : T(0);
-                T x[TR];
-                load_row<T, TR>(in + (size_t) i * TR, x);
-#pragma unroll
-                for (int r = 0; r < TR; r++) acc[r] = fma((ACC) w, (ACC) x[r], acc[r]);
-            }
+            accumulate_range<T, ACC, TR>(Wp, s_loop, s_lane, active ? j : 0, active, 0, n_loop, in, acc);
             if (active) epilogue(j, acc);
         }
         return;
@@ -85,14 +110,7 @@ __device__ __forceinline__ void dense_tile(const T* __restrict__ Wg, int n_lane,
     if (busy) {
         const int per = (n_loop + ks - 1) / ks;
         const int i0 = part * per, i1 = min(n_loop, i0 + per);
-#pragma unroll 4
-        for (int i = i0; i < i1; i++) {
-            const T w = active ? __ldg(Wg + (size_t) i * n_lane + j) : T(0);
-            T x[TR];
-            load_row<T, TR>(in + (size_t) i * TR, x);
-#pragma unroll
-            for (int r = 0; r < TR; r++) acc[r] = fma((ACC) w, (ACC) x[r], acc[r]);
-        }
+        accumulate_range<T, ACC, TR>(Wp, s_loop, s_lane, active ? j : 0, active, i0, i1, in, acc);
     }
     if (ks > 1) {
         if (busy && part > 0) {
@@ -129,6 +147,22 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
     double* cen = dzout + (size_t) nL * TR;                          // [TR][num_center]
     double* com = cen + (size_t) TR * net.num_center;                // [TR*3]
     double* scratch = com + TR * 3 + 1;                              // [kBatchWarps*TR*32] (as ACC)
+    T* wstage = reinterpret_cast<T*>(scratch + (size_t) kBatchWarps * TR * 32);   // [ws_total] weights, rows padded to an odd stride
+
+    // ---- weights that fit are staged in shared memory once per CTA: [n_out][odd stride] serves the forward
+    //      (lane = output row, stride odd -> conflict-free) and the backward (lane = input column) ----------------
+    const bool staged = args.ws_total > 0;
+    if (staged) {
+        for (int l = 0; l + 1 < L; l++) {
+            const int n_in = net.nodes[l], n_out = net.nodes[l + 1], ld = args.ws_ld[l];
+            const T* src = WeightsOf<T>::W(net) + net.w_off[l];
+            T* dst = wstage + args.ws_off[l];
+            for (int idx = tid; idx < n_in * n_out; idx += kBatchThreads) {
+                const int row = idx / n_in, col = idx - row * n_in;
+                dst[(size_t) row * ld + col] = __ldg(src + idx);
+            }
+        }
+    }
 
     // ---- umbrella centres of this tile -----------------------------------------------------------
     for (int idx = tid; idx < TR * net.num_center; idx += kBatchThreads) {
@@ -163,20 +197,22 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
     // ---- forward: calculate_output_of_each_layer, ANN_ReferenceKernels.cpp:179-260 --------------------
     for (int l = 0; l + 1 < L; l++) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
-        const T* Wt = WeightsOf<T>::Wt(net) + net.w_off[l];
+        // forward weight w(i = input, j = output): transposed global copy [n_in][n_out], or staged [n_out][ld]
+        const T* Wt = staged ? wstage + args.ws_off[l] : WeightsOf<T>::Wt(net) + net.w_off[l];
+        const size_t s_loop = staged ? 1 : (size_t) n_out, s_lane = staged ? (size_t) args.ws_ld[l] : 1;
         const T* b = WeightsOf<T>::b(net) + net.b_off[l];
         const T* in = act + (size_t) net.node_off[l] * TR;
         T* out = act + (size_t) net.node_off[l + 1] * TR;
         const int type = net.types[l];
         if (l + 2 == L) {
             // output layer: fp64 accumulation, pre-activations kept in fp64 for the head
-            dense_tile<T, double, TR>(Wt, n_out, n_in, in, scratch, [&](int j, const double (&acc)[TR]) {
+            dense_tile<T, double, TR>(Wt, s_loop, s_lane, n_out, n_in, in, scratch, [&](int j, const double (&acc)[TR]) {
                 const double bj = (double) b[j];
 #pragma unroll
                 for (int r = 0; r < TR; r++) zout[(size_t) j * TR + r] = acc[r] + bj;
             });
         } else if (type == ANNF_TANH || type == ANNF_LINEAR) {
-            dense_tile<T, T, TR>(Wt, n_out, n_in, in, reinterpret_cast<T*>(scratch), [&](int j, const T (&acc)[TR]) {
+            dense_tile<T, T, TR>(Wt, s_loop, s_lane, n_out, n_in, in, reinterpret_cast<T*>(scratch), [&](int j, const T (&acc)[TR]) {
                 const T bj = b[j];
 #pragma unroll
                 for (int r = 0; r < TR; r++) {
@@ -187,7 +223,7 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
         } else {
             // Circular / Softmax hidden layer: keep z, then transform the whole vector
             T* zbuf = extra + (size_t) args.x_off[l + 1] * TR;
-            dense_tile<T, T, TR>(Wt, n_out, n_in, in, reinterpret_cast<T*>(scratch), [&](int j, const T (&acc)[TR]) {
+            dense_tile<T, T, TR>(Wt, s_loop, s_lane, n_out, n_in, in, reinterpret_cast<T*>(scratch), [&](int j, const T (&acc)[TR]) {
                 const T bj = b[j];
 #pragma unroll
                 for (int r = 0; r < TR; r++) zbuf[(size_t) j * TR + r] = acc[r] + bj;
@@ -230,12 +266,14 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
     // ---- backward: back_prop, ANN_ReferenceKernels.cpp:299-373 --------------------------------------------
     for (int l = L - 2; l >= 0; l--) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
-        const T* W = WeightsOf<T>::W(net) + net.w_off[l];
+        // backward weight w(k = output, m = input): original copy [n_out][n_in], or staged [n_out][ld]
+        const T* W = staged ? wstage + args.ws_off[l] : WeightsOf<T>::W(net) + net.w_off[l];
+        const size_t s_loop = staged ? (size_t) args.ws_ld[l] : (size_t) n_in;
         const T* dz = act + (size_t) net.node_off[l + 1] * TR;     // dE/dz of layer l+1 (overwrote its activations)
         T* slot = act + (size_t) net.node_off[l] * TR;            // holds a_l, receives dE/dz_l (or dE/dx for l = 0)
         const int type = l >= 1 ? net.types[l - 1] : ANNF_LINEAR;
         if (type == ANNF_TANH || type == ANNF_LINEAR) {
-            dense_tile<T, T, TR>(W, n_in, n_out, dz, reinterpret_cast<T*>(scratch), [&](int m, const T (&acc)[TR]) {
+            dense_tile<T, T, TR>(W, s_loop, 1, n_in, n_out, dz, reinterpret_cast<T*>(scratch), [&](int m, const T (&acc)[TR]) {
 #pragma unroll
                 for (int r = 0; r < TR; r++) {
                     if (type == ANNF_TANH) {
@@ -249,7 +287,7 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
         } else {
             T* zbuf = extra + (size_t) args.x_off[l] * TR;
             T* dbuf = zbuf + (size_t) n_in * TR;
-            dense_tile<T, T, TR>(W, n_in, n_out, dz, reinterpret_cast<T*>(scratch), [&](int m, const T (&acc)[TR]) {
+            dense_tile<T, T, TR>(W, s_loop, 1, n_in, n_out, dz, reinterpret_cast<T*>(scratch), [&](int m, const T (&acc)[TR]) {
 #pragma unroll
                 for (int r = 0; r < TR; r++) dbuf[(size_t) m * TR + r] = acc[r];
             });
@@ -309,6 +347,17 @@ size_t batched_smem_bytes(const NetView& net, int extra_nodes, int tr, bool fp64
     return fp64 ? batched_smem_bytes<double>(net, extra_nodes, tr) : batched_smem_bytes<float>(net, extra_nodes, tr);
 }
 
+// Elements needed to stage every connection as [n_out][odd stride]; fills the per-connection offsets.
+static size_t staging_elements(const NetView& net, int* off, int* ld) {
+    size_t total = 0;
+    for (int l = 0; l + 1 < net.L; l++) {
+        ld[l] = net.nodes[l] | 1;
+        off[l] = (int) total;
+        total += (size_t) net.nodes[l + 1] * ld[l];
+    }
+    return total;
+}
+
 template <typename T, int TR>
 static cudaError_t launch_t(const BatchedArgs& args, size_t smem, cudaStream_t stream) {
     static bool configured[64] = {};
@@ -337,7 +386,14 @@ cudaError_t launch_batched(const NetView& net, const int* x_off, int extra_nodes
     args.energies = energies;
     for (int l = 0; l < kMaxLayers; l++) args.x_off[l] = x_off[l];
     args.extra_nodes = extra_nodes;
-    const size_t smem = batched_smem_bytes(net, extra_nodes, tr, fp64);
+    size_t smem = batched_smem_bytes(net, extra_nodes, tr, fp64);
+    const size_t stage = staging_elements(net, args.ws_off, args.ws_ld) * (fp64 ? sizeof(double) : sizeof(float));
+    if (smem + stage <= 200 * 1024) {
+        args.ws_total = (int) (stage / (fp64 ? sizeof(double) : sizeof(float)));
+        smem += stage;
+    } else {
+        args.ws_total = 0;
+    }
     if (fp64) {
         switch (tr) {
         case 8: return launch_t<double, 8>(args, smem, stream);

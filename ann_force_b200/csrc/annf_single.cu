@@ -12,8 +12,11 @@
 // contiguous slice of a layer's rows (forward) or columns (backward) and publishes the slice into
 // every peer's shared memory through DSMEM stores, followed by one cluster barrier.  Within a CTA a
 // forward row is a warp-wide dot product reduced with shuffles; a backward column is one thread
-// walking the (coalesced) weight rows.  Weights are read straight from L2/L1 (they are touched
-// exactly once per direction per evaluation, so staging them in shared memory would not save a byte).
+// walking the (coalesced) weight rows.
+// Small networks (one CTA): ALL weights and biases are pulled into shared memory by one cp.async burst
+// issued before the position gather, so the whole evaluation pays one global-memory round trip instead
+// of one per dependent loop (measured: the L2 round trips were ~70% of the kernel).  Wide networks (cluster):
+// weights stream from L2 (each is used once per direction).
 #include <cooperative_groups.h>
 
 #include "annf_common.cuh"
@@ -33,6 +36,7 @@ struct SingleArgs {
     int padded;
     void* energy;
     unsigned flags;
+    int red_doubles;            // size of the reduction / scratch region in doubles
 };
 
 // Position of one atom slot in nm, fp64, honouring single / mixed (+correction) / double layouts.
@@ -119,15 +123,40 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = net.L, total = net.node_off[L];
 
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double* a = smem;                 // activations  a[node_off[l] + j]
     double* z = a + total;            // pre-activations
     double* d = z + total;            // dE/dz (hidden/output layers), dE/dx (layer 0)
-    double* red = d + total;          // [8] small reductions / broadcasts
+    double* red = d + total;          // [8] small reductions / broadcasts, then scratch
     __shared__ double s_energy;
 
     // every CTA of the cluster must be resident before anyone stores into a peer's shared memory
     if (cl > 1) cluster.sync();
+
+    // umbrella centre and force constant: fetched now, needed only after the forward pass
+    __shared__ double s_k;
+    double* cen_s = red + args.red_doubles + ((3 * total + args.red_doubles) & 1);
+    for (int i = tid; i < net.num_center; i += kSingleThreads) cen_s[i] = net.center[i];
+    if (tid == 0) s_k = *net.k_dev;
+
+    // ---- one CTA: stage every weight and bias in shared memory (asynchronously) ---------------------
+    const double* Wbase = net.W64;
+    const double* bbase = net.b64;
+    if (cl == 1) {
+        const int nw = (int) net.w_off[L - 2] + net.nodes[L - 2] * net.nodes[L - 1];
+        const int nb = net.b_off[L - 2] + net.nodes[L - 1];
+        double* wsm = cen_s + net.num_center + (net.num_center & 1);                   // keep 16-byte alignment
+        double* bsm = wsm + nw + (nw & 1);
+        for (int i = 2 * tid; i + 1 < nw; i += 2 * kSingleThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(wsm + i)), "l"(net.W64 + i) : "memory");
+        for (int i = 2 * tid; i + 1 < nb; i += 2 * kSingleThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(bsm + i)), "l"(net.b64 + i) : "memory");
+        if (tid == 0 && (nw & 1)) wsm[nw - 1] = net.W64[nw - 1];
+        if (tid == 0 && (nb & 1)) bsm[nb - 1] = net.b64[nb - 1];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        Wbase = wsm;
+        bbase = bsm;
+    }
 
     // ---- feature stage: ANN_ReferenceKernels.cpp:128-151 (Cartesian) -------------------------
     // every CTA builds the full, centred input redundantly (it is 3*A values)
@@ -152,13 +181,14 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         __syncthreads();
         for (int i = tid; i < n0; i += kSingleThreads) a[i] -= red[i % 3];                // :143-145
     }
+    if (cl == 1) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
     // ---- forward: calculate_output_of_each_layer, ANN_ReferenceKernels.cpp:179-260 -------------
     for (int l = 0; l + 1 < L; l++) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
-        const double* W = net.W64 + net.w_off[l];
-        const double* b = net.b64 + net.b_off[l];
+        const double* W = Wbase + net.w_off[l];
+        const double* b = bbase + net.b_off[l];
         const double* ain = a + net.node_off[l];
         double* zout = z + net.node_off[l + 1];
         const int per = (n_out + cl - 1) / cl;
@@ -171,7 +201,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int j = jb + u * kSingleWarps;
-                    if (j < j1) acc[u] = fma(__ldg(W + (size_t) j * n_in + i), x, acc[u]);
+                    if (j < j1) acc[u] = fma(W[(size_t) j * n_in + i], x, acc[u]);
                 }
             }
 #pragma unroll
@@ -191,15 +221,14 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     // ---- energy + output-layer gradient (fp64, one thread per CTA, identical in every CTA) -----
     if (tid == 0) {
         const int n_last = net.nodes[L - 1];
-        s_energy = output_head(net.types[L - 2], n_last, z + net.node_off[L - 1], 1, net.center, *net.k_dev,
-                               d + net.node_off[L - 1], 1);
+        s_energy = output_head(net.types[L - 2], n_last, z + net.node_off[L - 1], 1, cen_s, s_k, d + net.node_off[L - 1], 1);
     }
     __syncthreads();
 
     // ---- backward: back_prop, ANN_ReferenceKernels.cpp:299-373 ----------------------------------
     for (int l = L - 2; l >= 0; l--) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
-        const double* W = net.W64 + net.w_off[l];
+        const double* W = Wbase + net.w_off[l];
         const double* dz = d + net.node_off[l + 1];
         double* dout = d + net.node_off[l];
         const int per = (n_in + cl - 1) / cl;
@@ -208,12 +237,14 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
             int k = 0;
             for (; k + 4 <= n_out; k += 4) {
-                acc0 = fma(__ldg(W + (size_t) (k + 0) * n_in + m), dz[k + 0], acc0);
-                acc1 = fma(__ldg(W + (size_t) (k + 1) * n_in + m), dz[k + 1], acc1);
-                acc2 = fma(__ldg(W + (size_t) (k + 2) * n_in + m), dz[k + 2], acc2);
-                acc3 = fma(__ldg(W + (size_t) (k + 3) * n_in + m), dz[k + 3], acc3);
+                const double w0 = W[(size_t) (k + 0) * n_in + m], w1 = W[(size_t) (k + 1) * n_in + m];
+                const double w2 = W[(size_t) (k + 2) * n_in + m], w3 = W[(size_t) (k + 3) * n_in + m];
+                acc0 = fma(w0, dz[k + 0], acc0);
+                acc1 = fma(w1, dz[k + 1], acc1);
+                acc2 = fma(w2, dz[k + 2], acc2);
+                acc3 = fma(w3, dz[k + 3], acc3);
             }
-            for (; k < n_out; k++) acc0 = fma(__ldg(W + (size_t) k * n_in + m), dz[k], acc0);
+            for (; k < n_out; k++) acc0 = fma(W[(size_t) k * n_in + m], dz[k], acc0);
             const double v = (acc0 + acc1) + (acc2 + acc3);
             if (cl == 1) {
                 dout[m] = v;
@@ -250,16 +281,26 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         }
     }
     if (rank == 0 && tid == 0 && args.energy != nullptr && !(args.flags & ANNF_FLAG_SKIP_ENERGY)) {
-        if (args.flags & ANNF_FLAG_ENERGY_DOUBLE) reinterpret_cast<double*>(args.energy)[0] += s_energy;
-        else reinterpret_cast<float*>(args.energy)[0] += (float) s_energy;
+        // fire-and-forget reduction instead of a load + store round trip at the tail of the kernel
+        if (args.flags & ANNF_FLAG_ENERGY_DOUBLE) atomicAdd(reinterpret_cast<double*>(args.energy), s_energy);
+        else atomicAdd(reinterpret_cast<float*>(args.energy), (float) s_energy);
     }
 }
 
-size_t single_smem_bytes(const NetView& net) {
-    const int total = net.node_off[net.L];
+static int single_red_doubles(const NetView& net) {
     int max_n = 0;
     for (int l = 0; l < net.L; l++) max_n = net.nodes[l] > max_n ? net.nodes[l] : max_n;
-    return sizeof(double) * (3 * (size_t) total + 8 + (size_t) (max_n > 3 * kSingleWarps ? max_n : 3 * kSingleWarps));
+    return 8 + (max_n > 3 * kSingleWarps ? max_n : 3 * kSingleWarps);
+}
+
+size_t single_smem_bytes(const NetView& net, int cluster_size) {
+    const int total = net.node_off[net.L];
+    size_t doubles = 3 * (size_t) total + single_red_doubles(net) + 1 + net.num_center + 1;
+    if (cluster_size == 1) {   // all weights + biases staged in shared memory
+        const int L = net.L;
+        doubles += (size_t) net.w_off[L - 2] + (size_t) net.nodes[L - 2] * net.nodes[L - 1] + net.b_off[L - 2] + net.nodes[L - 1] + 4;
+    }
+    return sizeof(double) * doubles;
 }
 
 cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq, const void* posq_corr,
@@ -272,10 +313,15 @@ cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq
     args.padded = padded;
     args.energy = energy;
     args.flags = flags;
+    args.red_doubles = single_red_doubles(net);
+    if (cluster_size == 1) {   // plain launch: no cluster attribute on the latency-critical small-network path
+        annf_single_kernel<<<1, kSingleThreads, single_smem_bytes(net, 1), stream>>>(args);
+        return cudaGetLastError();
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cluster_size);
     cfg.blockDim = dim3(kSingleThreads);
-    cfg.dynamicSmemBytes = single_smem_bytes(net);
+    cfg.dynamicSmemBytes = single_smem_bytes(net, cluster_size);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
