@@ -327,8 +327,8 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
             if (batched_smem_bytes(net, h->extra_nodes, tr, fp64) <= 200 * 1024) return tr;
         return 0;
     };
-    h->tile_fp64 = pick_tile(true);
-    h->tile_fp32 = pick_tile(false);
+    h->tile_fp64 = net.nodes[L - 1] <= 256 ? pick_tile(true) : 0;    // the fused kernel's head scratch holds 256 outputs
+    h->tile_fp32 = net.nodes[L - 1] <= 256 ? pick_tile(false) : 0;
     int prec = desc->precision;
     std::string why_not;
     if (prec == ANNF_PREC_AUTO || prec == ANNF_PREC_TF32X3) {

@@ -249,12 +249,20 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
         __syncthreads();
     }
 
-    // ---- fp64 head: energy + dE/dz of the output layer (one thread per replica) -------------------------
-    if (tid < TR) {
-        const int rr = r0 + tid;
-        const double e = output_head(net.types[L - 2], nL, zout + tid, TR, cen + (size_t) tid * net.num_center,
-                                     *net.k_dev, dzout + tid, TR);
-        if (rr < args.R) args.energies[rr] = e;
+    // ---- fp64 head: energy + dE/dz of the output layer; one thread per (replica, output or Circular pair) --------
+    {
+        double* eterm = scratch;                                     // [TR][nL] energy terms
+        for (int idx = tid; idx < TR * nL; idx += kBatchThreads) {
+            const int r = idx / nL, t = idx - r * nL;
+            eterm[idx] = output_head_parallel(net.types[L - 2], nL, zout + r, TR, cen + (size_t) r * net.num_center, *net.k_dev,
+                                              dzout + r, TR, t);
+        }
+        __syncthreads();
+        if (tid < TR && r0 + tid < args.R) {
+            double e = 0.0;
+            for (int t = 0; t < nL; t++) e += eterm[tid * nL + t];
+            args.energies[r0 + tid] = e;
+        }
     }
     __syncthreads();
     {

@@ -120,4 +120,18 @@ __device__ inline double output_head(int type, int n, const double* z, int zs, c
     return e;
 }
 
+// The same head, spread over the threads of a CTA for the element-wise output types: thread t < n handles
+// output t (Tanh / Linear) or pair t < n/2 (Circular) and returns ITS energy term; Softmax stays on thread 0.
+// Callers sum the returned terms (fixed order) to get the energy.
+__device__ inline double output_head_parallel(int type, int n, const double* z, int zs, const double* center, double k,
+                                              double* dz, int ds, int t) {
+    if (type == ANNF_SOFTMAX) return t == 0 ? output_head(type, n, z, zs, center, k, dz, ds) : 0.0;
+    if (type == ANNF_CIRCULAR) {
+        if (t >= n / 2) return 0.0;
+        return output_head(type, 2, z + (size_t) 2 * t * zs, zs, center + t, k, dz + (size_t) 2 * t * ds, ds);
+    }
+    if (t >= n) return 0.0;
+    return output_head(type, 1, z + (size_t) t * zs, zs, center + t, k, dz + (size_t) t * ds, ds);
+}
+
 }  // namespace annf

@@ -218,10 +218,19 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         }
     }
 
-    // ---- energy + output-layer gradient (fp64, one thread per CTA, identical in every CTA) -----
-    if (tid == 0) {
+    // ---- energy + output-layer gradient (fp64; one output or Circular pair per thread; identical in every CTA) -----
+    {
         const int n_last = net.nodes[L - 1];
-        s_energy = output_head(net.types[L - 2], n_last, z + net.node_off[L - 1], 1, cen_s, s_k, d + net.node_off[L - 1], 1);
+        double* eterm = red + 8;
+        for (int t = tid; t < n_last; t += kSingleThreads)
+            eterm[t] = output_head_parallel(net.types[L - 2], n_last, z + net.node_off[L - 1], 1, cen_s, s_k,
+                                            d + net.node_off[L - 1], 1, t);
+        __syncthreads();
+        if (tid == 0) {
+            double e = 0.0;
+            for (int t = 0; t < n_last; t++) e += eterm[t];
+            s_energy = e;
+        }
     }
     __syncthreads();
 

@@ -66,6 +66,7 @@ struct GemmParams {
     const float* row_mean;            // [M][4] mean input-gradient per component (EPI_FORCE)
     const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
     float neg_inv_scale;              // -1 / scaling_factor (EPI_FORCE)
+    int dry;                          // experiments (ANNF_TENSOR_DRY=1): return immediately, to measure the launch floor
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -167,26 +168,24 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
         return;
     }
     if (p.epi == EPI_FORCE) {
-        // column n = 3 * atom + component: F = -(g - mean_component) / s   (ANN_ReferenceKernels.cpp:397-410,
-        // the O(A^2) Jacobian loop collapsed into one mean per component)
+        // column n = 3 * atom + component: F = -(g - mean_component) / s = g * (-1/s) + mean_component / s
+        // (ANN_ReferenceKernels.cpp:397-410, the O(A^2) Jacobian loop collapsed into one mean per component)
         const float4 mu = __ldg(reinterpret_cast<const float4*>(p.row_mean) + m);
-        const float mean[3] = {mu.x, mu.y, mu.z};
-        const float g[4] = {v.x, v.y, v.z, v.w};
-        float f[4];
-        int c = n % 3;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            f[j] = (g[j] - mean[c]) * p.neg_inv_scale;
-            c = c == 2 ? 0 : c + 1;
-        }
+        const float k = p.neg_inv_scale;
+        const int c0 = n % 3;                                   // component of the first of the four columns
+        const float ma = -k * (c0 == 0 ? mu.x : (c0 == 1 ? mu.y : mu.z));      // mean/s for column n, n+3
+        const float mb = -k * (c0 == 0 ? mu.y : (c0 == 1 ? mu.z : mu.x));      // ... n+1
+        const float mc = -k * (c0 == 0 ? mu.z : (c0 == 1 ? mu.x : mu.y));      // ... n+2
+        const float4 f = make_float4(fmaf(v.x, k, ma), fmaf(v.y, k, mb), fmaf(v.z, k, mc), fmaf(v.w, k, ma));
         float* row = p.out_hi + (size_t) m * p.ld_out;
         if (p.sel_atoms == nullptr) {
-            *reinterpret_cast<float4*>(row + n) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(row + n) = f;
         } else {
+            const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int e = n + j, atom = e / 3;
-                row[(size_t) __ldg(p.sel_atoms + atom) * 3 + (e - 3 * atom)] = f[j];
+                row[(size_t) __ldg(p.sel_atoms + atom) * 3 + (e - 3 * atom)] = fv[j];
             }
         }
         return;
@@ -235,6 +234,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
 
     pdl_launch_dependents();                                // the next kernel may start its own prologue now
+    if (p.dry & 1) return;
     if (warp == kEpiWarps && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
         for (int s = 0; s < kStages; s++) {
@@ -268,6 +268,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     const uint32_t ph = (uint32_t) (i / kStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free
                     const uint32_t full = smem_u32(&bar_full[s]);
+                    if (p.dry & 4) {                                              // experiments: no TMA traffic
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+                        continue;
+                    }
                     mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
                     const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
                     const int kc = (kb0 + i) * BK;
@@ -303,6 +307,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + BN * BK * 4;
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                            if (p.dry & 2) break;                                  // experiments: no tensor-core work
                             const uint32_t off = kk * UMMA_K * 4;                  // 32 bytes along K inside the swizzle span
                             const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
                             const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
@@ -363,15 +368,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     if (S > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();                                                            // every partial tile is parked
-        if (warp < kEpiWarps) {
+        // BN = 128: every thread of the CTA takes part (the producer / MMA / spare warps are idle by now);
+        // BN = 256: only the epilogue warps (the other warpgroup gave its registers away with setmaxnreg)
+        constexpr int kReduceThreads = BN >= 256 ? 32 * kEpiWarps : Cfg::kThreads;
+        if ((int) threadIdx.x < kReduceThreads) {
             constexpr int kRows = BM / S;                                          // rows this CTA reduces
             constexpr int kVecPerRow = BN / 4;
-            const int t = threadIdx.x;                                             // 0 .. 32 * kEpiWarps - 1
+            const int t = threadIdx.x;
             float* staging = reinterpret_cast<float*>(data);
             const float* peer[S];
 #pragma unroll
             for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, r);
-            for (int v = t; v < kRows * kVecPerRow; v += 32 * kEpiWarps) {
+            for (int v = t; v < kRows * kVecPerRow; v += kReduceThreads) {
                 const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -403,13 +411,14 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     extern __shared__ float xs[];                           // [3 * A]
     pdl_launch_dependents();
     pdl_wait();
+    if (contiguous & 2) return;                             // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = net.n_sel, n0 = 3 * A;
     const float* base = coords + (size_t) r * N * 3;
     __shared__ double red[8][3];
     __shared__ double com[3];
     double s[3] = {0.0, 0.0, 0.0};
-    if (contiguous) {
+    if (contiguous & 1) {
         // selection is atoms 0..A-1 and rows are 16-byte aligned: straight vector copy, component = index % 3
         const float4* src = reinterpret_cast<const float4*>(base);
         for (int v = tid; v < n0 / 4; v += 256) {
@@ -474,6 +483,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
                                                            float* __restrict__ d_hi, float* __restrict__ d_lo, double* __restrict__ energies) {
     pdl_launch_dependents();
     pdl_wait();
+    if (R < 0) return;                                      // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = net.L, nH = net.nodes[L - 2], nL = net.nodes[L - 1];
     __shared__ double part[4][kHeadMaxOut];
@@ -503,8 +513,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     __syncthreads();
     if (tid < nL) zs[tid] = ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + b[tid];
     __syncthreads();
-    if (tid == 0) energies[r] = output_head(net.types[L - 2], nL, zs, 1, cen, *net.k_dev, dzs, 1);
+    // energy + output gradient: one output (or Circular pair) per thread, terms summed in a fixed order
+    if (tid < kHeadMaxOut) part[0][tid] = output_head_parallel(net.types[L - 2], nL, zs, 1, cen, *net.k_dev, dzs, 1, tid);
     __syncthreads();
+    if (tid == 0) {
+        double e = 0.0;
+        for (int j = 0; j < nL; j++) e += part[0][j];
+        energies[r] = e;
+    }
     if (tid < nL) dzf[tid] = (float) dzs[tid];
     __syncthreads();
     const int hidden_type = net.types[L - 3];
@@ -531,6 +547,7 @@ __global__ void __launch_bounds__(128) colmean_kernel(int R, int K, int A, const
                                                      float* __restrict__ row_mean) {
     pdl_launch_dependents();
     pdl_wait();
+    if (R < 0) return;                                      // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double part[4][3];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -605,6 +622,8 @@ struct TensorPlan {
     double* wsum = nullptr;                         // [3][n_1]: sum over atoms of W_0[k][3i+c]
     bool sel_identity = false;                      // selection is atoms 0..A-1 in order
     int force_bn = 0;                               // ANNF_GEMM_BN=128|256 overrides the tile-width heuristic (experiments)
+    int force_split = 0;                            // ANNF_GEMM_SPLIT_SHORTK=1|2|4|8 overrides split-K for GEMMs with K <= 1024
+    int dry = 0;                                    // ANNF_TENSOR_DRY=1: every kernel returns at once (launch-floor measurement)
     std::vector<GemmOp> fwd, bwd;
 };
 
@@ -673,6 +692,8 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     TensorPlan* t = new TensorPlan();
     t->L = L;
     if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
+    if (const char* env = getenv("ANNF_GEMM_SPLIT_SHORTK")) t->force_split = atoi(env);
+    if (const char* env = getenv("ANNF_TENSOR_DRY")) t->dry = atoi(env);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -820,6 +841,7 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
                                float* forces, int atoms_per_replica) {
     GemmParams p = op.p;
     p.M = R;
+    p.dry = t->dry;
     if (p.epi == EPI_FORCE) {
         p.out_hi = forces;
         p.ld_out = 3 * atoms_per_replica;
@@ -834,7 +856,8 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
     int bn = tiles128 > t->sm_count ? 256 : 128;
     if (t->force_bn == 128 || t->force_bn == 256) bn = t->force_bn;
     const int tiles = ((p.N + bn - 1) / bn) * ((R + BM - 1) / BM);
-    const int s = pick_split(tiles, (p.K + BK - 1) / BK, t->sm_count);
+    int s = pick_split(tiles, (p.K + BK - 1) / BK, t->sm_count);
+    if (t->force_split > 0 && (p.K + BK - 1) / BK <= 32) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
     if (bn == 256) {
         switch (s) {
         case 8: return launch_gemm_t<256, 8>(op, p, stream);
@@ -866,7 +889,8 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
         return e;
     };
     err = timed("prep_kernel", [&] {
-        const int contiguous = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0;
+        const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
+                               (t->dry ? 2 : 0);
         return launch_pdl(prep_kernel, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 0, net, R, coords, atoms_per_replica,
                           t->x_hi[0], t->x_lo[0], t->ld[0], contiguous);
     });
@@ -877,14 +901,14 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
         if (err != cudaSuccess) return err;
     }
     err = timed("head_kernel", [&] {
-        return launch_pdl(head_kernel, dim3(R), dim3(kHeadThreads), 0, stream, 0, net, R, centers, (const float*) t->x_hi[L - 2],
+        return launch_pdl(head_kernel, dim3(R), dim3(kHeadThreads), 0, stream, 0, net, t->dry ? -R : R, centers, (const float*) t->x_hi[L - 2],
                           (const float*) t->x_lo[L - 2], t->ld[L - 2], t->d_hi[L - 2], t->d_lo[L - 2], energies);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : t->bwd) {
         if (op.p.epi == EPI_FORCE) {
             err = timed("colmean_kernel", [&] {
-                return launch_pdl(colmean_kernel, dim3(R), dim3(128), 0, stream, 0, R, t->nodes[1], net.n_sel, (const float*) t->d_hi[1],
+                return launch_pdl(colmean_kernel, dim3(R), dim3(128), 0, stream, 0, t->dry ? -R : R, t->nodes[1], net.n_sel, (const float*) t->d_hi[1],
                                   (const float*) t->d_lo[1], t->ld[1], (const double*) t->wsum, t->row_mean);
             });
             if (err != cudaSuccess) return err;
