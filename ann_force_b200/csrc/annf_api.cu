@@ -103,7 +103,7 @@ struct annf_context {
     // device allocations
     double *W64 = nullptr, *Wt64 = nullptr, *b64 = nullptr, *center = nullptr, *k_dev = nullptr, *staged = nullptr;
     float *W32 = nullptr, *Wt32 = nullptr, *b32 = nullptr;
-    int *sel_atoms = nullptr, *sel_slots = nullptr, *inverse = nullptr;
+    int *sel_atoms = nullptr, *sel_slots = nullptr, *inverse = nullptr, *pairs_local = nullptr, *dihedrals_local = nullptr;
     double* staged_host = nullptr;   // pinned, [num_center + 1]
     TensorPlan* tensor = nullptr;
     Profiler prof;
@@ -133,7 +133,7 @@ void release(annf_context* h) {
     if (h->tensor) tensor_plan_destroy(h->tensor);
     cudaFree(h->W64); cudaFree(h->Wt64); cudaFree(h->b64); cudaFree(h->center); cudaFree(h->k_dev); cudaFree(h->staged);
     cudaFree(h->W32); cudaFree(h->Wt32); cudaFree(h->b32);
-    cudaFree(h->sel_atoms); cudaFree(h->sel_slots); cudaFree(h->inverse);
+    cudaFree(h->sel_atoms); cudaFree(h->sel_slots); cudaFree(h->inverse); cudaFree(h->pairs_local); cudaFree(h->dihedrals_local);
     cudaFree(h->h_coords); cudaFree(h->h_centers); cudaFree(h->h_forces); cudaFree(h->h_energies);
     if (h->staged_host) cudaFreeHost(h->staged_host);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
@@ -200,11 +200,18 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
                 return fail(ANNF_ERR_INVALID, "index_of_backbone_atoms[%d] = %d is outside 1..%d (indices are 1-based)", i, a,
                             desc->num_system_atoms);
         }
-    } else if (desc->data_type_in_input_layer == ANNF_INPUT_DIHEDRAL_COS_SIN ||
-               desc->data_type_in_input_layer == ANNF_INPUT_PAIR_DISTANCES) {
-        // The legacy CUDA kernel threw for dihedral input as well (CudaANN_Kernels.cpp:257-260).
-        return fail(ANNF_ERR_UNSUPPORTED, "data_type_in_input_layer = %d is not implemented on the CUDA path yet (Cartesian = 1 is)",
-                    desc->data_type_in_input_layer);
+    } else if (desc->data_type_in_input_layer == ANNF_INPUT_DIHEDRAL_COS_SIN) {
+        if (desc->num_dihedrals <= 0 || !desc->dihedrals || 2 * desc->num_dihedrals != desc->num_of_nodes[0])
+            return fail(ANNF_ERR_INVALID, "dihedral input: 2 * %d dihedrals != %d input nodes", desc->num_dihedrals, desc->num_of_nodes[0]);
+        for (int i = 0; i < 4 * desc->num_dihedrals; i++)
+            if (desc->dihedrals[i] < 0 || desc->dihedrals[i] >= desc->num_system_atoms)
+                return fail(ANNF_ERR_INVALID, "dihedral atom index %d is outside the %d-atom system", desc->dihedrals[i], desc->num_system_atoms);
+    } else if (desc->data_type_in_input_layer == ANNF_INPUT_PAIR_DISTANCES) {
+        if (desc->num_pairs <= 0 || !desc->pairs || desc->num_pairs != desc->num_of_nodes[0])
+            return fail(ANNF_ERR_INVALID, "pair-distance input: %d pairs != %d input nodes", desc->num_pairs, desc->num_of_nodes[0]);   // CudaANN_Kernels.cpp:211
+        for (int i = 0; i < 2 * desc->num_pairs; i++)
+            if (desc->pairs[i] < 0 || desc->pairs[i] >= desc->num_system_atoms)
+                return fail(ANNF_ERR_INVALID, "pair atom index %d is outside the %d-atom system", desc->pairs[i], desc->num_system_atoms);
     } else {
         return fail(ANNF_ERR_INVALID, "data_type_in_input_layer = %d", desc->data_type_in_input_layer);
     }
@@ -263,8 +270,23 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     std::vector<float> W32(W64.begin(), W64.end()), Wt32(Wt64.begin(), Wt64.end()), b32(b64.begin(), b64.end());
     std::vector<double> center(desc->potential_center, desc->potential_center + desc->num_center);
     std::vector<double> kvec(1, desc->force_constant);
-    std::vector<int> sel(desc->num_backbone_atoms);
-    for (int i = 0; i < desc->num_backbone_atoms; i++) sel[i] = desc->index_of_backbone_atoms[i] - 1;   // ANN_ReferenceKernels.cpp:132
+    // feature atoms: the Cartesian selection as given, or the sorted union of the atoms of all pairs / dihedrals, with the
+    // pair / dihedral lists re-expressed as indices into that union
+    std::vector<int> sel, pairs_local, dihedrals_local;
+    if (desc->data_type_in_input_layer == ANNF_INPUT_CARTESIAN) {
+        sel.resize(desc->num_backbone_atoms);
+        for (int i = 0; i < desc->num_backbone_atoms; i++) sel[i] = desc->index_of_backbone_atoms[i] - 1;   // ANN_ReferenceKernels.cpp:132
+    } else {
+        const bool is_pairs = desc->data_type_in_input_layer == ANNF_INPUT_PAIR_DISTANCES;
+        const int* list = is_pairs ? desc->pairs : desc->dihedrals;
+        const int count = is_pairs ? 2 * desc->num_pairs : 4 * desc->num_dihedrals;
+        sel.assign(list, list + count);
+        std::sort(sel.begin(), sel.end());
+        sel.erase(std::unique(sel.begin(), sel.end()), sel.end());
+        std::vector<int>& local = is_pairs ? pairs_local : dihedrals_local;
+        local.resize(count);
+        for (int i = 0; i < count; i++) local[i] = (int) (std::lower_bound(sel.begin(), sel.end(), list[i]) - sel.begin());
+    }
 
 #define ANNF_CUDA_H(call)                                                                            \
     do {                                                                                             \
@@ -285,6 +307,8 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     ANNF_CUDA_H(upload(&h->k_dev, kvec));
     ANNF_CUDA_H(upload(&h->sel_atoms, sel));
     ANNF_CUDA_H(upload(&h->sel_slots, sel));
+    ANNF_CUDA_H(upload(&h->pairs_local, pairs_local));
+    ANNF_CUDA_H(upload(&h->dihedrals_local, dihedrals_local));
     ANNF_CUDA_H(cudaMalloc((void**) &h->inverse, sizeof(int) * h->num_system_atoms));
     ANNF_CUDA_H(cudaMalloc((void**) &h->staged, sizeof(double) * (desc->num_center + 1)));
     ANNF_CUDA_H(cudaMallocHost((void**) &h->staged_host, sizeof(double) * (desc->num_center + 1)));
@@ -293,10 +317,10 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     net.center = h->center; net.k_dev = h->k_dev; net.num_center = desc->num_center;
     net.scale = desc->scaling_factor;
     net.input_type = desc->data_type_in_input_layer;
-    net.n_sel = desc->num_backbone_atoms;
+    net.n_sel = (int) sel.size();
     net.sel_atoms = h->sel_atoms; net.sel_slots = h->sel_slots;
-    net.n_pairs = 0; net.pairs = nullptr; net.pair_slots = nullptr;
-    net.n_dihedrals = 0; net.dihedrals = nullptr; net.dihedral_slots = nullptr;
+    net.n_pairs = (int) pairs_local.size() / 2; net.pairs = h->pairs_local;
+    net.n_dihedrals = (int) dihedrals_local.size() / 4; net.dihedrals = h->dihedrals_local;
 
     // ---- kernel selection ---------------------------------------------------------------------------------
     // single replica: fp64 always (latency-bound; B200 fp64 FMA is half rate, parity is ~1e-12)

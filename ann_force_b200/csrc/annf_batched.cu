@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
     double* cen = dzout + (size_t) nL * TR;                          // [TR][num_center]
     double* com = cen + (size_t) TR * net.num_center;                // [TR*3]
     double* scratch = com + TR * 3 + 1;                              // [kBatchWarps*TR*32] (as ACC)
-    T* wstage = reinterpret_cast<T*>(scratch + (size_t) kBatchWarps * TR * 32);   // [ws_total] weights, rows padded to an odd stride
+    const int n_fpos = net.input_type == ANNF_INPUT_CARTESIAN ? 0 : 3 * net.n_sel;
+    double* fpos = scratch + (size_t) kBatchWarps * TR * 32;         // [3*n_feat][TR] positions of the feature atoms (pair / dihedral inputs)
+    double* facc = fpos + (size_t) n_fpos * TR;                      // [3*n_feat][TR] per-atom force accumulators
+    T* wstage = reinterpret_cast<T*>(facc + (size_t) n_fpos * TR);   // [ws_total] weights, rows padded to an odd stride
 
     // ---- weights that fit are staged in shared memory once per CTA: [n_out][odd stride] serves the forward
     //      (lane = output row, stride odd -> conflict-free) and the backward (lane = input column) ----------------
@@ -171,26 +174,61 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
         cen[idx] = args.centers ? (double) args.centers[(size_t) rr * net.num_center + c] : net.center[c];
     }
 
-    // ---- feature stage (Cartesian): ANN_ReferenceKernels.cpp:128-151 --------------------------------
     const int A = net.n_sel;
-    for (int p = warp; p < TR * 3; p += kBatchWarps) {
-        const int r = p / 3, c = p - 3 * r, rr = r0 + r;
-        double s = 0.0;
-        if (rr < args.R) {
-            const float* base = args.coords + (size_t) rr * N * 3;
-            for (int i = lane; i < A; i += 32) s += (double) __ldg(base + (size_t) net.sel_atoms[i] * 3 + c) / scale;
+    if (net.input_type == ANNF_INPUT_CARTESIAN) {
+        // ---- feature stage (Cartesian): ANN_ReferenceKernels.cpp:128-151 --------------------------------
+        for (int p = warp; p < TR * 3; p += kBatchWarps) {
+            const int r = p / 3, c = p - 3 * r, rr = r0 + r;
+            double s = 0.0;
+            if (rr < args.R) {
+                const float* base = args.coords + (size_t) rr * N * 3;
+                for (int i = lane; i < A; i += 32) s += (double) __ldg(base + (size_t) net.sel_atoms[i] * 3 + c) / scale;
+            }
+            s = warp_sum(s);
+            if (lane == 0) com[p] = s / A;                                // unweighted centroid (:137-141)
         }
-        s = warp_sum(s);
-        if (lane == 0) com[p] = s / A;                                // unweighted centroid (:137-141)
-    }
-    __syncthreads();
-    for (int idx = tid; idx < n0 * TR; idx += kBatchThreads) {
-        const int r = idx / n0, i = idx - r * n0, rr = r0 + r;
-        const int atom = i / 3, c = i - 3 * atom;
-        double v = 0.0;
-        if (rr < args.R)
-            v = (double) __ldg(args.coords + ((size_t) rr * N + net.sel_atoms[atom]) * 3 + c) / scale - com[r * 3 + c];
-        act[(size_t) i * TR + r] = (T) v;
+        __syncthreads();
+        for (int idx = tid; idx < n0 * TR; idx += kBatchThreads) {
+            const int r = idx / n0, i = idx - r * n0, rr = r0 + r;
+            const int atom = i / 3, c = i - 3 * atom;
+            double v = 0.0;
+            if (rr < args.R)
+                v = (double) __ldg(args.coords + ((size_t) rr * N + net.sel_atoms[atom]) * 3 + c) / scale - com[r * 3 + c];
+            act[(size_t) i * TR + r] = (T) v;
+        }
+    } else {
+        // ---- pair distances (:152-160) / dihedral cos, sin (:125-127, :579-636): stage the feature atoms -------
+        for (int idx = tid; idx < n_fpos * TR; idx += kBatchThreads) {
+            const int r = idx / n_fpos, i = idx - r * n_fpos, rr = min(r0 + r, args.R - 1);
+            const int atom = i / 3, c = i - 3 * atom;
+            fpos[(size_t) i * TR + r] = (double) __ldg(args.coords + ((size_t) rr * N + net.sel_atoms[atom]) * 3 + c);
+            facc[(size_t) i * TR + r] = 0.0;
+        }
+        __syncthreads();
+        if (net.input_type == ANNF_INPUT_PAIR_DISTANCES) {
+            const double inv = 1.0 / scale;
+            for (int idx = tid; idx < net.n_pairs * TR; idx += kBatchThreads) {
+                const int p = idx / TR, r = idx - p * TR;
+                const int i0 = net.pairs[2 * p], i1 = net.pairs[2 * p + 1];
+                double d2 = 0.0;
+                for (int c = 0; c < 3; c++) {
+                    const double d = fpos[(size_t) (3 * i0 + c) * TR + r] * inv - fpos[(size_t) (3 * i1 + c) * TR + r] * inv;
+                    d2 += d * d;
+                }
+                act[(size_t) p * TR + r] = (T) sqrt(d2);
+            }
+        } else {
+            for (int idx = tid; idx < net.n_dihedrals * TR; idx += kBatchThreads) {
+                const int q = idx / TR, r = idx - q * TR;
+                double pt[4][3];
+                for (int k = 0; k < 4; k++)
+                    for (int c = 0; c < 3; c++) pt[k][c] = fpos[(size_t) (3 * net.dihedrals[4 * q + k] + c) * TR + r];
+                double cs, sn;
+                dihedral_cos_sin(pt[0], pt[1], pt[2], pt[3], cs, sn);
+                act[(size_t) (2 * q) * TR + r] = (T) cs;
+                act[(size_t) (2 * q + 1) * TR + r] = (T) sn;
+            }
+        }
     }
     __syncthreads();
 
@@ -324,21 +362,59 @@ __global__ void __launch_bounds__(kBatchThreads) annf_batched_kernel(const Batch
         __syncthreads();
     }
 
-    // ---- forces: ANN_ReferenceKernels.cpp:397-410 (centring Jacobian as one mean, O(A)) -----------------
-    for (int p = warp; p < TR * 3; p += kBatchWarps) {
-        const int r = p / 3, c = p - 3 * r;
-        double s = 0.0;
-        for (int i = lane; i < A; i += 32) s += (double) act[(size_t) (3 * i + c) * TR + r];
-        s = warp_sum(s);
-        if (lane == 0) com[p] = s / A;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < n0 * TR; idx += kBatchThreads) {
-        const int r = idx / n0, i = idx - r * n0, rr = r0 + r;
-        if (rr >= args.R) continue;
-        const int atom = i / 3, c = i - 3 * atom;
-        const double f = -((double) act[(size_t) i * TR + r] - com[r * 3 + c]) / scale;
-        args.forces[((size_t) rr * N + net.sel_atoms[atom]) * 3 + c] = (float) f;
+    if (net.input_type == ANNF_INPUT_CARTESIAN) {
+        // ---- forces: ANN_ReferenceKernels.cpp:397-410 (centring Jacobian as one mean, O(A)) -----------------
+        for (int p = warp; p < TR * 3; p += kBatchWarps) {
+            const int r = p / 3, c = p - 3 * r;
+            double s = 0.0;
+            for (int i = lane; i < A; i += 32) s += (double) act[(size_t) (3 * i + c) * TR + r];
+            s = warp_sum(s);
+            if (lane == 0) com[p] = s / A;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n0 * TR; idx += kBatchThreads) {
+            const int r = idx / n0, i = idx - r * n0, rr = r0 + r;
+            if (rr >= args.R) continue;
+            const int atom = i / 3, c = i - 3 * atom;
+            const double f = -((double) act[(size_t) i * TR + r] - com[r * 3 + c]) / scale;
+            args.forces[((size_t) rr * N + net.sel_atoms[atom]) * 3 + c] = (float) f;
+        }
+    } else {
+        // ---- forces for pair (:411-421) / dihedral (:392-396, :425-577) inputs: accumulate per feature atom, then write -----
+        if (net.input_type == ANNF_INPUT_PAIR_DISTANCES) {
+            for (int idx = tid; idx < net.n_pairs * TR; idx += kBatchThreads) {
+                const int p = idx / TR, r = idx - p * TR;
+                const int i0 = net.pairs[2 * p], i1 = net.pairs[2 * p + 1];
+                double d[3], d2 = 0.0;
+                for (int c = 0; c < 3; c++) {
+                    d[c] = fpos[(size_t) (3 * i0 + c) * TR + r] - fpos[(size_t) (3 * i1 + c) * TR + r];
+                    d2 += d[c] * d[c];
+                }
+                const double f = (double) act[(size_t) p * TR + r] / (scale * sqrt(d2));
+                for (int c = 0; c < 3; c++) {
+                    atomicAdd(&facc[(size_t) (3 * i0 + c) * TR + r], -d[c] * f);
+                    atomicAdd(&facc[(size_t) (3 * i1 + c) * TR + r], d[c] * f);
+                }
+            }
+        } else {
+            for (int idx = tid; idx < net.n_dihedrals * TR; idx += kBatchThreads) {
+                const int q = idx / TR, r = idx - q * TR;
+                double pt[4][3], f[4][3];
+                for (int k = 0; k < 4; k++)
+                    for (int c = 0; c < 3; c++) pt[k][c] = fpos[(size_t) (3 * net.dihedrals[4 * q + k] + c) * TR + r];
+                dihedral_forces(pt[0], pt[1], pt[2], pt[3], (double) act[(size_t) (2 * q) * TR + r],
+                                (double) act[(size_t) (2 * q + 1) * TR + r], f);
+                for (int k = 0; k < 4; k++)
+                    for (int c = 0; c < 3; c++) atomicAdd(&facc[(size_t) (3 * net.dihedrals[4 * q + k] + c) * TR + r], f[k][c]);
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n_fpos * TR; idx += kBatchThreads) {
+            const int r = idx / n_fpos, i = idx - r * n_fpos, rr = r0 + r;
+            if (rr >= args.R) continue;
+            const int atom = i / 3, c = i - 3 * atom;
+            args.forces[((size_t) rr * N + net.sel_atoms[atom]) * 3 + c] = (float) facc[(size_t) i * TR + r];
+        }
     }
 }
 
@@ -347,8 +423,9 @@ static size_t batched_smem_bytes(const NetView& net, int extra_nodes, int tr) {
     const size_t total = net.node_off[net.L];
     const size_t nL = net.nodes[net.L - 1];
     const size_t t_bytes = (sizeof(T) * (total + extra_nodes) * tr + 15) & ~(size_t) 15;
+    const size_t n_fpos = net.input_type == ANNF_INPUT_CARTESIAN ? 0 : 3 * (size_t) net.n_sel;
     return t_bytes + sizeof(double) * (2 * nL * tr + (size_t) tr * net.num_center + tr * 3 + 1)
-           + sizeof(double) * kBatchWarps * tr * 32;
+           + sizeof(double) * kBatchWarps * tr * 32 + sizeof(double) * 2 * n_fpos * tr;
 }
 
 size_t batched_smem_bytes(const NetView& net, int extra_nodes, int tr, bool fp64) {

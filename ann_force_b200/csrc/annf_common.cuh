@@ -30,15 +30,14 @@ struct NetView {
     int num_center;
     double scale;                   // scaling_factor
     int input_type;
-    int n_sel;                      // selected atoms (Cartesian)
-    const int* sel_atoms;           // 0-based original atom index per selected atom
-    const int* sel_slots;           // position-buffer slot per selected atom (OpenMM reordering)
+    int n_sel;                      // atoms this force reads: the Cartesian selection, or the union of the atoms of all
+                                    // pairs / dihedrals ("feature atoms")
+    const int* sel_atoms;           // 0-based original atom index per feature atom
+    const int* sel_slots;           // position-buffer slot per feature atom (OpenMM reordering)
     int n_pairs;
-    const int* pairs;               // 0-based original atom indices, [2*n_pairs]
-    const int* pair_slots;
+    const int* pairs;               // [2*n_pairs] indices INTO the feature-atom list
     int n_dihedrals;
-    const int* dihedrals;           // [4*n_dihedrals]
-    const int* dihedral_slots;
+    const int* dihedrals;           // [4*n_dihedrals] indices INTO the feature-atom list
 };
 
 template <typename T> struct WeightsOf;
@@ -118,6 +117,69 @@ __device__ inline double output_head(int type, int n, const double* z, int zs, c
         }
     }
     return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dihedral featuriser (data_type_in_input_layer == 0), fp64.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void v3sub(const double* a, const double* b, double* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+__device__ __forceinline__ double v3dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void v3cross(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// sign convention of the reference: (sum of components of n1 x n2) * (sum of components of the middle bond) > 0
+// (ANN_ReferenceKernels.cpp:456,612)
+__device__ __forceinline__ int dihedral_sign(const double* n1xn2, const double* d2) {
+    return (n1xn2[0] + n1xn2[1] + n1xn2[2]) * (d2[0] + d2[1] + d2[2]) > 0 ? 1 : -1;
+}
+
+// cos / sin of the dihedral p0-p1-p2-p3: get_cos_and_sin_for_four_atoms, ANN_ReferenceKernels.cpp:599-636
+// (normals normalised by multiplying with the reciprocal norm, like OpenMM's Vec3::operator/=)
+__device__ inline void dihedral_cos_sin(const double* p0, const double* p1, const double* p2, const double* p3, double& c, double& s) {
+    double d1[3], d2[3], d3[3], n1[3], n2[3], sv[3];
+    v3sub(p1, p0, d1); v3sub(p2, p1, d2); v3sub(p3, p2, d3);
+    v3cross(d1, d2, n1); v3cross(d2, d3, n2);
+    const double r1 = 1.0 / sqrt(v3dot(n1, n1)), r2 = 1.0 / sqrt(v3dot(n2, n2));
+    for (int i = 0; i < 3; i++) { n1[i] *= r1; n2[i] *= r2; }
+    c = v3dot(n1, n2);
+    v3cross(n1, n2, sv);
+    s = sqrt(v3dot(sv, sv)) * dihedral_sign(sv, d2);
+}
+
+// Force contributions of one dihedral from dE/dcos, dE/dsin: the chain rule of
+// get_force_from_derivative_of_first_layer (ANN_ReferenceKernels.cpp:425-577) in vector form:
+//   cos = n1.n2/(|n1||n2|), sin = sign |n1 x n2|/(|n1||n2|), n1 = d1 x d2, n2 = d2 x d3;
+//   dE/dd1 = d2 x g1, dE/dd2 = g1 x d1 + d3 x g2, dE/dd3 = g2 x d2  with g1 = dE/dn1, g2 = dE/dn2;
+//   force[atom k] += dE/dd_k, force[atom k+1] -= dE/dd_k (:546-553).   f[4][3] receives the four contributions.
+__device__ inline void dihedral_forces(const double* p0, const double* p1, const double* p2, const double* p3,
+                                       double g_cos, double g_sin, double (&f)[4][3]) {
+    double d1[3], d2[3], d3[3], n1[3], n2[3], c[3];
+    v3sub(p1, p0, d1); v3sub(p2, p1, d2); v3sub(p3, p2, d3);
+    v3cross(d1, d2, n1); v3cross(d2, d3, n2); v3cross(n1, n2, c);
+    const int sign = dihedral_sign(c, d2);
+    const double a = v3dot(n1, n1), b = v3dot(n2, n2), n1n2 = v3dot(n1, n2), cc = v3dot(c, c);
+    const double la = sqrt(a), lb = sqrt(b), lc = sqrt(cc);
+    double n2xc[3], cxn1[3], g1[3], g2[3];
+    v3cross(n2, c, n2xc); v3cross(c, n1, cxn1);
+    for (int i = 0; i < 3; i++) {
+        const double dcos_dn1 = n2[i] / (la * lb) - n1[i] * n1n2 / (a * la * lb);
+        const double dcos_dn2 = n1[i] / (la * lb) - n2[i] * n1n2 / (b * la * lb);
+        const double dsin_dn1 = sign * (n2xc[i] / (lc * la * lb) - n1[i] * lc / (a * la * lb));
+        const double dsin_dn2 = sign * (cxn1[i] / (lc * la * lb) - n2[i] * lc / (b * la * lb));
+        g1[i] = g_cos * dcos_dn1 + g_sin * dsin_dn1;
+        g2[i] = g_cos * dcos_dn2 + g_sin * dsin_dn2;
+    }
+    double e1[3], e2a[3], e2b[3], e3[3];
+    v3cross(d2, g1, e1);
+    v3cross(g1, d1, e2a); v3cross(d3, g2, e2b);
+    v3cross(g2, d2, e3);
+    for (int i = 0; i < 3; i++) {
+        const double e2 = e2a[i] + e2b[i];
+        f[0][i] = e1[i];
+        f[1][i] = e2 - e1[i];
+        f[2][i] = e3[i] - e2;
+        f[3][i] = -e3[i];
+    }
 }
 
 // The same head, spread over the threads of a CTA for the element-wise output types: thread t < n handles

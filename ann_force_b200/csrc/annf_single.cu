@@ -138,6 +138,10 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     double* cen_s = red + args.red_doubles + ((3 * total + args.red_doubles) & 1);
     for (int i = tid; i < net.num_center; i += kSingleThreads) cen_s[i] = net.center[i];
     if (tid == 0) s_k = *net.k_dev;
+    // pair / dihedral inputs: feature-atom positions and a per-atom force accumulator
+    const int n_fpos = net.input_type == ANNF_INPUT_CARTESIAN ? 0 : 3 * net.n_sel;
+    double* fpos = cen_s + net.num_center + (net.num_center & 1);
+    double* facc = fpos + n_fpos;
 
     // ---- one CTA: stage every weight and bias in shared memory (asynchronously) ---------------------
     const double* Wbase = net.W64;
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     if (cl == 1) {
         const int nw = (int) net.w_off[L - 2] + net.nodes[L - 2] * net.nodes[L - 1];
         const int nb = net.b_off[L - 2] + net.nodes[L - 1];
-        double* wsm = cen_s + net.num_center + (net.num_center & 1);                   // keep 16-byte alignment
+        double* wsm = facc + n_fpos;                                                    // 2 * n_fpos is even: stays 16-byte aligned
         double* bsm = wsm + nw + (nw & 1);
         for (int i = 2 * tid; i + 1 < nw; i += 2 * kSingleThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(wsm + i)), "l"(net.W64 + i) : "memory");
@@ -180,6 +184,29 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         }
         __syncthreads();
         for (int i = tid; i < n0; i += kSingleThreads) a[i] -= red[i % 3];                // :143-145
+    } else {
+        // pair distances (:152-160) or dihedral cos / sin (:125-127, :579-636): stage the feature atoms' positions
+        double* pos_s = fpos;
+        for (int i = tid; i < net.n_sel; i += kSingleThreads) {
+            const double3 p = load_pos(args, net.sel_slots[i]);
+            pos_s[3 * i] = p.x; pos_s[3 * i + 1] = p.y; pos_s[3 * i + 2] = p.z;
+            facc[3 * i] = 0.0; facc[3 * i + 1] = 0.0; facc[3 * i + 2] = 0.0;
+        }
+        __syncthreads();
+        if (net.input_type == ANNF_INPUT_PAIR_DISTANCES) {
+            for (int p = tid; p < net.n_pairs; p += kSingleThreads) {
+                const double* pa = pos_s + 3 * net.pairs[2 * p];
+                const double* pb = pos_s + 3 * net.pairs[2 * p + 1];
+                const double inv = 1.0 / net.scale;                                       // Vec3 / scalar multiplies by the reciprocal
+                const double dx = pa[0] * inv - pb[0] * inv, dy = pa[1] * inv - pb[1] * inv, dz = pa[2] * inv - pb[2] * inv;
+                a[p] = sqrt(dx * dx + dy * dy + dz * dz);
+            }
+        } else {
+            for (int q = tid; q < net.n_dihedrals; q += kSingleThreads) {
+                const int* id = net.dihedrals + 4 * q;
+                dihedral_cos_sin(pos_s + 3 * id[0], pos_s + 3 * id[1], pos_s + 3 * id[2], pos_s + 3 * id[3], a[2 * q], a[2 * q + 1]);
+            }
+        }
     }
     if (cl == 1) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -289,6 +316,35 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
                       (unsigned long long) ((long long) (f * (double) 0x100000000LL)));
         }
     }
+    if (!(args.flags & ANNF_FLAG_SKIP_FORCES) && net.input_type != ANNF_INPUT_CARTESIAN && rank == 0) {
+        // get_all_forces_from_derivative_of_first_layer: dihedral branch :392-396 (+ :425-577), pair branch :411-421.
+        // Contributions are summed per feature atom in shared memory first, then one fixed-point atomicAdd per component.
+        const double* g = d;
+        const double* pos_s = fpos;
+        if (net.input_type == ANNF_INPUT_PAIR_DISTANCES) {
+            for (int p = tid; p < net.n_pairs; p += kSingleThreads) {
+                const int i0 = net.pairs[2 * p], i1 = net.pairs[2 * p + 1];
+                const double dx = pos_s[3 * i0] - pos_s[3 * i1], dy = pos_s[3 * i0 + 1] - pos_s[3 * i1 + 1], dz = pos_s[3 * i0 + 2] - pos_s[3 * i1 + 2];
+                const double f = g[p] / (net.scale * sqrt(dx * dx + dy * dy + dz * dz));
+                atomicAdd(&facc[3 * i0], -dx * f); atomicAdd(&facc[3 * i0 + 1], -dy * f); atomicAdd(&facc[3 * i0 + 2], -dz * f);
+                atomicAdd(&facc[3 * i1], dx * f); atomicAdd(&facc[3 * i1 + 1], dy * f); atomicAdd(&facc[3 * i1 + 2], dz * f);
+            }
+        } else {
+            for (int q = tid; q < net.n_dihedrals; q += kSingleThreads) {
+                const int* id = net.dihedrals + 4 * q;
+                double f[4][3];
+                dihedral_forces(pos_s + 3 * id[0], pos_s + 3 * id[1], pos_s + 3 * id[2], pos_s + 3 * id[3], g[2 * q], g[2 * q + 1], f);
+                for (int k = 0; k < 4; k++)
+                    for (int c = 0; c < 3; c++) atomicAdd(&facc[3 * id[k] + c], f[k][c]);
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < 3 * net.n_sel; t += kSingleThreads) {
+            const int i = t / 3, c = t - 3 * i;
+            atomicAdd(&args.force[net.sel_slots[i] + c * args.padded],
+                      (unsigned long long) ((long long) (facc[t] * (double) 0x100000000LL)));
+        }
+    }
     if (rank == 0 && tid == 0 && args.energy != nullptr && !(args.flags & ANNF_FLAG_SKIP_ENERGY)) {
         // fire-and-forget reduction instead of a load + store round trip at the tail of the kernel
         if (args.flags & ANNF_FLAG_ENERGY_DOUBLE) atomicAdd(reinterpret_cast<double*>(args.energy), s_energy);
@@ -305,6 +361,7 @@ static int single_red_doubles(const NetView& net) {
 size_t single_smem_bytes(const NetView& net, int cluster_size) {
     const int total = net.node_off[net.L];
     size_t doubles = 3 * (size_t) total + single_red_doubles(net) + 1 + net.num_center + 1;
+    if (net.input_type != ANNF_INPUT_CARTESIAN) doubles += 6 * (size_t) net.n_sel;      // feature-atom positions + force accumulator
     if (cluster_size == 1) {   // all weights + biases staged in shared memory
         const int L = net.L;
         doubles += (size_t) net.w_off[L - 2] + (size_t) net.nodes[L - 2] * net.nodes[L - 1] + net.b_off[L - 2] + net.nodes[L - 1] + 4;

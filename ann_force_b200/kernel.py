@@ -65,7 +65,8 @@ class CalcANNForce:
         self._device = device
         self._num_center = int(center.size)
         self._num_system_atoms = int(num_system_atoms)
-        self._n_sel = int(atoms.size)
+        # atoms whose force rows the kernels write: the Cartesian selection; for pair / dihedral inputs a subset we do not track here
+        self._n_sel = int(atoms.size) if force.get_data_type_in_input_layer() == 1 else -1
 
     def close(self) -> None:
         if self._handle:

@@ -54,7 +54,7 @@ enum { ANNF_PREC_AUTO = 0, ANNF_PREC_FP64 = 1, ANNF_PREC_FP32 = 2, ANNF_PREC_TF3
 typedef enum {
     ANNF_OK = 0,
     ANNF_ERR_INVALID = 1,       /* bad argument / inconsistent description */
-    ANNF_ERR_UNSUPPORTED = 2,   /* valid in the reference, not implemented on this path (message says which) */
+    ANNF_ERR_UNSUPPORTED = 2,   /* valid in the reference, not available on the requested path (message says which) */
     ANNF_ERR_CUDA = 3,          /* a CUDA runtime call failed; message carries cudaGetErrorString */
     ANNF_ERR_NO_DEVICE = 4      /* no CUDA device: there is NO CPU fallback */
 } annf_status;

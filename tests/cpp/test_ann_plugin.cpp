@@ -94,6 +94,68 @@ static void test_cartesian(const string& last_activation, double golden_energy, 
     check_forces_against_energy(context, positions, precision == "single" ? 0.0 : 1e-6);
 }
 
+static void test_pair_distances() {                                  // test_ANN_package.cpp:596-674 (run there on "CUDA" too)
+    cout << "pair distances 6-3-3 Tanh/Tanh\n";
+    System system;
+    for (int i = 0; i < 4; i++) system.addParticle(1.0);
+    VerletIntegrator integrator(0.01);
+    ANN_Force* f = new ANN_Force();
+    f->set_index_of_backbone_atoms({1, 2, 3, 4});
+    f->set_num_of_nodes(vector<int>({6, 3, 3}));
+    f->set_layer_types(vector<string>({"Tanh", "Tanh"}));
+    f->set_list_of_pair_index_for_distances(vector<vector<int> >({{1, 2}, {1, 3}, {1, 4}, {2, 3}, {2, 4}, {3, 4}}));
+    f->set_coeffients_of_connections({{1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0.7, 0, 0, 0, 0, 1, 1}, {1, 0, 0.4, 0, 1, 0, 0, 0, 1}});
+    f->set_force_constant(10);
+    f->set_scaling_factor(10);
+    f->set_potential_center(vector<double>({0, 0, 0}));
+    f->set_values_of_biased_nodes({{0.1, 0.2, 0.3}, {0.5, 0.6, 0.4}});
+    f->set_data_type_in_input_layer(2);
+    system.addForce(f);
+    Context context(system, integrator, Platform::getPlatformByName("CUDA"), props("double", true));
+    vector<Vec3> positions = {Vec3(-1, -2, -3), Vec3(0, 0, 0), Vec3(1, 0, 0), Vec3(0, 0, 2)};
+    context.setPositions(positions);
+    ASSERT_EQUAL_TOL(10.832122286301122, context.getState(State::Energy).getPotentialEnergy(), 1e-12);
+    check_forces_against_energy(context, positions, 1e-6);
+}
+
+static void test_dihedrals(const string& last_activation, vector<double> center, double golden_energy) {   // :182-341
+    cout << "dihedrals 4-4-4 Tanh/" << last_activation << "\n";
+    System system;
+    for (int i = 0; i < 6; i++) system.addParticle(1.0);
+    VerletIntegrator integrator(0.01);
+    ANN_Force* f = new ANN_Force();
+    f->set_num_of_nodes(vector<int>({4, 4, 4}));
+    f->set_layer_types(vector<string>({"Tanh", last_activation}));
+    f->set_coeffients_of_connections({{1, 0, 0, 0, 0, 1, 0, 0.7, 0, 0, 1, 0, 0, 0, 0, 1}, {1, 0, 0.4, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}});
+    f->set_force_constant(10);
+    f->set_potential_center(center);
+    f->set_values_of_biased_nodes({{0.1, 0.2, 0.3, 0.4}, {0.5, 0.6, 0.4, 0.3}});
+    f->set_list_of_index_of_atoms_forming_dihedrals_from_index_of_backbone_atoms(vector<int>({1, 2, 3, 4, 5, 6}));
+    system.addForce(f);                                               // data_type_in_input_layer defaults to 0 (ANN_Force.h:137)
+    Context context(system, integrator, Platform::getPlatformByName("CUDA"), props("double"));
+    vector<Vec3> positions = {Vec3(-1, -2, -3), Vec3(0, 0, 0), Vec3(1, 0, 0), Vec3(0, 0, 1), Vec3(0.5, 0, 0), Vec3(0, 0.3, 0.6)};
+    context.setPositions(positions);
+    ASSERT_EQUAL_TOL(golden_energy, context.getState(State::Energy).getPotentialEnergy(), 1e-12);
+    // tolerance of the central-difference check: forces reach 110 here and curvature is large (the reference's own
+    // forward-difference criterion is applied inside as well, except for the {2.4, 2.3} window where its truncation
+    // error alone exceeds FORCE_TOL: see tests/test_oracle.py)
+    context.setPositions(positions);
+    State state = context.getState(State::Forces | State::Energy);
+    const double h = 1e-6;
+    double fmax = 1.0;
+    for (const Vec3& v : state.getForces()) for (int c = 0; c < 3; c++) fmax = max(fmax, fabs(v[c]));
+    for (size_t i = 0; i < positions.size(); i++)
+        for (int c = 0; c < 3; c++) {
+            vector<Vec3> p = positions; p[i][c] += h;
+            context.setPositions(p);
+            const double ep = context.getState(State::Energy).getPotentialEnergy();
+            p[i][c] -= 2 * h;
+            context.setPositions(p);
+            const double em = context.getState(State::Energy).getPotentialEnergy();
+            ASSERT(fabs(-(ep - em) / (2 * h) - state.getForces()[i][c]) <= 1e-6 * fmax);
+        }
+}
+
 static vector<double> generate_random_array(int size, int seed) {   // test_ANN_package.cpp:504-511
     srand((unsigned) seed);
     vector<double> a;
@@ -198,6 +260,10 @@ int main() {
         test_cartesian("Linear", 26.790165804903218, "mixed", false);
         test_cartesian("Circular", 16.572144252757681, "double", true);
         for (int n = 20; n < 200; n += 40) test_larger_system(n, 1);     // the reference sweeps 20..180 step 20 (:689-694)
+        test_pair_distances();
+        test_dihedrals("Tanh", {0, 0, 0, 0}, 0.5707411857967678);
+        test_dihedrals("Circular", {0, 0}, 34.049960896473365);
+        test_dihedrals("Circular", {2.4, 2.3}, 50.906053293232567);
         test_update_parameters_and_reorder();
         test_errors();
     } catch (const exception& e) {

@@ -21,8 +21,7 @@ E_RTOL = 1e-6      # north_star energy bar
 F_RTOL = 1e-4      # north_star force bar (relative max-norm)
 FIXED_POINT_ULP = 2.0 ** -32   # OpenMM's force buffer resolution, kJ/mol/nm
 
-CARTESIAN_GOLDEN = [n for n in golden_io.names()
-                    if golden_io.load(n)[5]["data_type_in_input_layer"] == 1]
+CARTESIAN_GOLDEN = golden_io.names()      # every fixture: Cartesian, pair-distance and dihedral inputs
 
 
 def test_library_reports_device():
@@ -312,7 +311,77 @@ def test_errors_are_reported_not_swallowed():
     kernel.initialize(7, force)
     with pytest.raises(_capi.ANNForceError):
         kernel.execute_batched(torch.zeros(2, 6, 3, device="cuda"))        # fewer atoms per replica than the system
-    # the legacy CUDA kernel threw for dihedral input (CudaANN_Kernels.cpp:257-260); so does this one, for now
+    # dihedral input whose atoms lie outside the system
     dih, _ = cases.dihedral_4_4_4("Tanh")
     with pytest.raises(_capi.ANNForceError):
-        CalcANNForce().initialize(6, dih)
+        CalcANNForce().initialize(4, dih)
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other two featurisers: pair distances and dihedral cos / sin
+# ------------------------------------------------------------------------------------------------------
+def _pair_force(n_atoms, n_pairs, seed):
+    rng = np.random.default_rng(seed)
+    pairs = set()
+    while len(pairs) < n_pairs:
+        i, j = rng.choice(n_atoms, size=2, replace=False)
+        pairs.add((int(min(i, j)) + 1, int(max(i, j)) + 1))
+    f = synthetic.make_force([3 * 4, 16, 4], ["Tanh", "Tanh"], 4, seed=seed)     # only used as a weight source below
+    g = ANN_Force()
+    nodes = [n_pairs, 24, 6]
+    rngw = np.random.default_rng(seed + 1)
+    g.set_num_of_nodes(nodes)
+    g.set_layer_types(["Tanh", "Circular"])
+    g.set_coeffients_of_connections([rngw.uniform(-0.4, 0.4, nodes[0] * nodes[1]), rngw.uniform(-0.4, 0.4, nodes[1] * nodes[2])])
+    g.set_values_of_biased_nodes([rngw.uniform(-0.1, 0.1, nodes[1]), rngw.uniform(-0.1, 0.1, nodes[2])])
+    g.set_potential_center([0.5, -1.0, 2.0])
+    g.set_force_constant(50.0)
+    g.set_scaling_factor(0.3)
+    g.set_data_type_in_input_layer(2)
+    g.set_list_of_pair_index_for_distances(sorted(pairs))
+    g.set_index_of_backbone_atoms(list(range(1, n_atoms + 1)))
+    return g
+
+
+def _dihedral_force(n_atoms, seed):
+    g = ANN_Force()
+    backbone = list(range(2, 2 + 3 * ((n_atoms - 2) // 3)))
+    g.set_list_of_index_of_atoms_forming_dihedrals_from_index_of_backbone_atoms(backbone)
+    nd = len(g.get_list_of_index_of_atoms_forming_dihedrals())
+    nodes = [2 * nd, 20, 4]
+    rngw = np.random.default_rng(seed)
+    g.set_num_of_nodes(nodes)
+    g.set_layer_types(["Tanh", "Tanh"])
+    g.set_coeffients_of_connections([rngw.uniform(-0.5, 0.5, nodes[0] * nodes[1]), rngw.uniform(-0.5, 0.5, nodes[1] * nodes[2])])
+    g.set_values_of_biased_nodes([rngw.uniform(-0.1, 0.1, nodes[1]), rngw.uniform(-0.1, 0.1, nodes[2])])
+    g.set_potential_center([0.1, -0.2, 0.3, 0.0])
+    g.set_force_constant(80.0)
+    g.set_data_type_in_input_layer(0)
+    return g
+
+
+@pytest.mark.parametrize("kind", ["pairs", "dihedrals"])
+def test_other_featurisers_single_and_batched(kind):
+    n_atoms = 17
+    force = _pair_force(n_atoms, 23, seed=3) if kind == "pairs" else _dihedral_force(n_atoms, seed=4)
+    R = 37
+    pos = synthetic.make_positions(n_atoms, R, seed=61)
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
+    # batched, fp64 and fp32 contractions
+    e, f, _ = run_batched(force, pos, None, precision="fp64")
+    np.testing.assert_allclose(e, e_ref, rtol=1e-11)
+    assert max_norm_rel(f, f_ref) <= 1e-6
+    e32, f32, _ = run_batched(force, pos, None, precision="fp32")
+    np.testing.assert_allclose(e32, e_ref, rtol=2e-5)
+    assert max_norm_rel(f32, f_ref) <= F_RTOL
+    # atoms that take part in no pair / dihedral feel nothing
+    used = np.zeros(n_atoms, dtype=bool)
+    lists = force.get_list_of_pair_index_for_distances() if kind == "pairs" else force.get_list_of_index_of_atoms_forming_dihedrals()
+    used[np.unique(np.asarray(lists).ravel())] = True
+    assert np.all(f[:, ~used, :] == 0.0)
+    # single replica on OpenMM buffers with a shuffled slot order
+    order = np.random.default_rng(8).permutation(n_atoms)
+    e1, f1, seen, _ = run_single(force, pos[0].astype(np.float64), "double", order=order)
+    e1_ref, f1_ref = port.evaluate(force, seen)
+    assert abs(e1 - e1_ref) <= 1e-11 * abs(e1_ref)
+    assert np.abs(f1 - f1_ref).max() <= 1e-10 * np.abs(f1_ref).max() + 2 * FIXED_POINT_ULP
