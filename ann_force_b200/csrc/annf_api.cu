@@ -32,7 +32,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
 void tensor_plan_destroy(TensorPlan* plan);
 cudaError_t tensor_plan_run(TensorPlan* plan, Profiler* prof, const NetView& net, int R,
                             const float* coords, int atoms_per_replica, const float* centers, float* forces,
-                            double* energies, cudaStream_t stream, long long* launches);
+                            double* energies, cudaStream_t stream, long long* launches, int slot_index);
 }  // namespace annf
 
 using namespace annf;
@@ -106,9 +106,10 @@ struct annf_context {
     int *sel_atoms = nullptr, *sel_slots = nullptr, *inverse = nullptr, *pairs_local = nullptr, *dihedrals_local = nullptr;
     double* staged_host = nullptr;   // pinned, [num_center + 1]
     TensorPlan* tensor = nullptr;
+    int tensor_slot = 0;             // which activation-buffer set of the tensor plan the next batched call uses
     Profiler prof;
     // host-buffer entry
-    cudaStream_t host_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    cudaStream_t host_stream = nullptr, host_stream2 = nullptr, in_stream = nullptr, out_stream = nullptr;
     cudaEvent_t ev_in[8] = {}, ev_comp[8] = {};
     float *h_coords = nullptr, *h_centers = nullptr, *h_forces = nullptr;
     double* h_energies = nullptr;
@@ -137,6 +138,7 @@ void release(annf_context* h) {
     cudaFree(h->h_coords); cudaFree(h->h_centers); cudaFree(h->h_forces); cudaFree(h->h_energies);
     if (h->staged_host) cudaFreeHost(h->staged_host);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->host_stream2) cudaStreamDestroy(h->host_stream2);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
     if (h->out_stream) cudaStreamDestroy(h->out_stream);
     for (int i = 0; i < 8; i++) {
@@ -378,6 +380,7 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
         return fail(ANNF_ERR_UNSUPPORTED, "network too large for the fused batched kernel's shared memory in this precision");
     }
     ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking));
     ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
     ANNF_CUDA_H(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) {
@@ -469,7 +472,8 @@ annf_status annf_eval_batched(annf_handle h, int32_t R, const float* coords, int
     cudaStream_t s = (cudaStream_t) stream;
     cudaError_t err;
     if (h->batched_path == 1) {
-        err = tensor_plan_run(h->tensor, &h->prof, h->net, R, coords, atoms_per_replica, centers, forces, energies, s, &h->launches);
+        err = tensor_plan_run(h->tensor, &h->prof, h->net, R, coords, atoms_per_replica, centers, forces, energies, s, &h->launches,
+                              h->tensor_slot);
     } else {
         const bool fp64 = h->prec_batched == ANNF_PREC_FP64;
         h->prof.begin(fp64 ? "annf_batched_kernel<f64>" : "annf_batched_kernel<f32>", s);
@@ -506,7 +510,8 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
         h->h_cap_energies = R;
     }
     // Software pipeline over replica chunks: the copy-in of chunk c+1 and the copy-out of chunk c-1 overlap
-    // the evaluation of chunk c (PCIe is full duplex; three streams ordered by events).
+    // the evaluation of chunk c (PCIe is full duplex; streams ordered by events).  Consecutive chunks evaluate on
+    // two compute streams with separate activation buffers, so their latency-bound kernels overlap as well.
     int chunks = 1;
     {
         const size_t bytes = sizeof(float) * n_coords;
@@ -517,29 +522,49 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
     }
     const size_t row = (size_t) atoms_per_replica * 3;
     const bool zero_fill = h->net.n_sel != atoms_per_replica;   // kernels write the selected atoms only
+    // Chunk sizes DEcrease (weights chunks+1, chunks, ..., 2): the copy-in stream is the long pole, so what remains after
+    // its last byte lands — evaluating and copying out the LAST chunk — should be as short as possible.
+    int bounds[9];
+    {
+        const long long total_w = (long long) chunks * (chunks + 3) / 2;
+        long long acc = 0;
+        bounds[0] = 0;
+        for (int c = 0; c < chunks; c++) {
+            acc += chunks + 1 - c;
+            bounds[c + 1] = (int) ((long long) R * acc / total_w);
+        }
+        bounds[chunks] = R;
+        for (int c = 0; c < chunks; c++) if (bounds[c + 1] <= bounds[c]) bounds[c + 1] = std::min(R, bounds[c] + 1);
+    }
     for (int c = 0; c < chunks; c++) {
-        const int r0 = (int) ((long long) R * c / chunks), r1 = (int) ((long long) R * (c + 1) / chunks), n = r1 - r0;
+        const int r0 = bounds[c], r1 = bounds[c + 1], n = r1 - r0;
+        if (n <= 0) continue;
         ANNF_CUDA(cudaMemcpyAsync(h->h_coords + r0 * row, coords_host + r0 * row, sizeof(float) * n * row, cudaMemcpyHostToDevice, h->in_stream));
         if (centers_host)
             ANNF_CUDA(cudaMemcpyAsync(h->h_centers + (size_t) r0 * h->net.num_center, centers_host + (size_t) r0 * h->net.num_center,
                                       sizeof(float) * n * h->net.num_center, cudaMemcpyHostToDevice, h->in_stream));
+        cudaStream_t compute = (c & 1) ? h->host_stream2 : h->host_stream;
+        h->tensor_slot = c & 1;
         ANNF_CUDA(cudaEventRecord(h->ev_in[c], h->in_stream));
-        ANNF_CUDA(cudaStreamWaitEvent(h->host_stream, h->ev_in[c], 0));
-        if (zero_fill) ANNF_CUDA(cudaMemsetAsync(h->h_forces + r0 * row, 0, sizeof(float) * n * row, h->host_stream));
+        ANNF_CUDA(cudaStreamWaitEvent(compute, h->ev_in[c], 0));
+        if (zero_fill) ANNF_CUDA(cudaMemsetAsync(h->h_forces + r0 * row, 0, sizeof(float) * n * row, compute));
         annf_status st = annf_eval_batched(h, n, h->h_coords + r0 * row, atoms_per_replica,
                                            centers_host ? h->h_centers + (size_t) r0 * h->net.num_center : nullptr,
-                                           h->h_forces + r0 * row, h->h_energies + r0, h->host_stream);
+                                           h->h_forces + r0 * row, h->h_energies + r0, compute);
+        h->tensor_slot = 0;
         if (st != ANNF_OK) {
-            cudaStreamSynchronize(h->in_stream); cudaStreamSynchronize(h->host_stream); cudaStreamSynchronize(h->out_stream);
+            cudaStreamSynchronize(h->in_stream); cudaStreamSynchronize(h->host_stream); cudaStreamSynchronize(h->host_stream2);
+            cudaStreamSynchronize(h->out_stream);
             return st;
         }
-        ANNF_CUDA(cudaEventRecord(h->ev_comp[c], h->host_stream));
+        ANNF_CUDA(cudaEventRecord(h->ev_comp[c], compute));
         ANNF_CUDA(cudaStreamWaitEvent(h->out_stream, h->ev_comp[c], 0));
         ANNF_CUDA(cudaMemcpyAsync(forces_host + r0 * row, h->h_forces + r0 * row, sizeof(float) * n * row, cudaMemcpyDeviceToHost, h->out_stream));
         ANNF_CUDA(cudaMemcpyAsync(energies_host + r0, h->h_energies + r0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->out_stream));
     }
     ANNF_CUDA(cudaStreamSynchronize(h->out_stream));
     ANNF_CUDA(cudaStreamSynchronize(h->host_stream));
+    ANNF_CUDA(cudaStreamSynchronize(h->host_stream2));
     ANNF_CUDA(cudaStreamSynchronize(h->in_stream));
     return ANNF_OK;
 }

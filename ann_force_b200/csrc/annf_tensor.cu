@@ -147,11 +147,14 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = tf32_round(v - hi);
 }
 
-template <int BN> struct GemmCfg {
+// CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computes a 256 x BN tile, each CTA holding 128 rows of A
+// and BN/2 rows of B; the leader CTA issues every MMA and both CTAs' tensor cores execute it.
+template <int BN, int CG> struct GemmCfg {
     static constexpr int kEpiWarps = BN / 32;                                   // each owns 32 TMEM lanes x 128 columns
     static constexpr int kThreads = (kEpiWarps + 4) * 32;                       // + producer warp, MMA warp, 2 idle (warpgroup padding)
-    static constexpr int kStageBytes = (2 * BM + 2 * BN) * BK * 4;
-    static constexpr int kStages = BN >= 256 ? 2 : 3;
+    static constexpr int kBRows = BN / CG;                                      // rows of B this CTA stages
+    static constexpr int kStageBytes = (2 * BM + 2 * kBRows) * BK * 4;
+    static constexpr int kStages = kStageBytes > 80 * 1024 ? 2 : 3;
     static constexpr int kStagingLd = BN + 4;                                   // fp32 elements, padded against bank conflicts
     static constexpr int kStagingBytes = BM * kStagingLd * 4;
     static constexpr int kDataBytes = kStageBytes * kStages > kStagingBytes ? kStageBytes * kStages : kStagingBytes;
@@ -161,8 +164,60 @@ template <int BN> struct GemmCfg {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// One epilogue element group: 4 consecutive columns of one output row.
-__device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int n, float4 v) {
+// ---- cta_group::2 flavours of the PTX wrappers -------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; completes its bytes on the mbarrier at `bar_cluster` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once the MMAs issued so far retire) on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (m >> 4) << 24);
+}
+
+// One epilogue element group = 4 consecutive columns of one output row, in two steps so that callers can issue the global
+// loads of several groups before any of the dependent math (the epilogue loop is otherwise bound by one L2 round trip per group).
+struct EpiAux { float4 a, b; };
+
+__device__ __forceinline__ EpiAux epilogue_load(const GemmParams& p, int m, int n) {
+    EpiAux x;
+    x.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    x.b = x.a;
+    if (p.epi == EPI_FORCE) {
+        x.a = __ldg(reinterpret_cast<const float4*>(p.row_mean) + m);
+    } else if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
+        x.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    } else if (p.epi == EPI_TANH_GRAD) {
+        x.a = __ldg(reinterpret_cast<const float4*>(p.aux_hi + (size_t) m * p.ld_aux + n));
+        x.b = __ldg(reinterpret_cast<const float4*>(p.aux_lo + (size_t) m * p.ld_aux + n));
+    }
+    return x;
+}
+
+__device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int n, float4 v, const EpiAux& x) {
     if (p.epi == EPI_STORE) {
         *reinterpret_cast<float4*>(p.out_hi + (size_t) m * p.ld_out + n) = v;
         return;
@@ -170,7 +225,7 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
     if (p.epi == EPI_FORCE) {
         // column n = 3 * atom + component: F = -(g - mean_component) / s = g * (-1/s) + mean_component / s
         // (ANN_ReferenceKernels.cpp:397-410, the O(A^2) Jacobian loop collapsed into one mean per component)
-        const float4 mu = __ldg(reinterpret_cast<const float4*>(p.row_mean) + m);
+        const float4 mu = x.a;
         const float k = p.neg_inv_scale;
         const int c0 = n % 3;                                   // component of the first of the four columns
         const float ma = -k * (c0 == 0 ? mu.x : (c0 == 1 ? mu.y : mu.z));      // mean/s for column n, n+3
@@ -191,13 +246,10 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
         return;
     }
     if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        v.x += x.a.x; v.y += x.a.y; v.z += x.a.z; v.w += x.a.w;
         if (p.epi == EPI_BIAS_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
     } else if (p.epi == EPI_TANH_GRAD) {
-        const float4 ah = __ldg(reinterpret_cast<const float4*>(p.aux_hi + (size_t) m * p.ld_aux + n));
-        const float4 al = __ldg(reinterpret_cast<const float4*>(p.aux_lo + (size_t) m * p.ld_aux + n));
-        const float a0 = ah.x + al.x, a1 = ah.y + al.y, a2 = ah.z + al.z, a3 = ah.w + al.w;
+        const float a0 = x.a.x + x.b.x, a1 = x.a.y + x.b.y, a2 = x.a.z + x.b.z, a3 = x.a.w + x.b.w;
         v.x *= (1.f - a0 * a0); v.y *= (1.f - a1 * a1); v.z *= (1.f - a2 * a2); v.w *= (1.f - a3 * a3);
     }
     float4 hi, lo;
@@ -206,18 +258,77 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
     *reinterpret_cast<float4*>(p.out_lo + (size_t) m * p.ld_out + n) = lo;
 }
 
-template <int BN, int S>
-__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
+// Cooperative epilogue over the parked tile(s): thread t of kGroupThreads walks (row, 4-column) groups with consecutive lanes
+// along a row — 512-byte coalesced global accesses — summing the S split-K partials (own + peers', through DSMEM) in a fixed
+// order, with the auxiliary global loads of four groups issued ahead of the dependent math.
+template <int BN, int S, int CG, int kGroupThreads>
+__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
+    using Cfg = GemmCfg<BN, CG>;
+    constexpr int kRows = BM / S;                                                  // rows this CTA finishes
+    constexpr int kVecPerRow = BN / 4;
+    float* staging = reinterpret_cast<float*>(data);
+    const float* peer[S];
+    if (S > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, pair_rank + CG * r);   // same pair position, split r
+    } else {
+        peer[0] = staging;
+    }
+    constexpr int kGroups = (kRows * kVecPerRow + kGroupThreads - 1) / kGroupThreads;   // groups per thread
+    constexpr int kBatch = 4;
+#pragma unroll 1
+    for (int g0 = 0; g0 < kGroups; g0 += kBatch) {
+        EpiAux aux[kBatch];
+        float4 sum[kBatch];
+        int mm[kBatch], nn[kBatch];
+        bool ok[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {                                         // all the loads of the batch first
+            const int v = t + (g0 + u) * kGroupThreads;
+            const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
+            mm[u] = m0 + row; nn[u] = n0 + col;
+            ok[u] = (g0 + u) < kGroups && v < kRows * kVecPerRow && mm[u] < p.M && nn[u] < p.N;
+            sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) {
+                aux[u] = epilogue_load(p, mm[u], nn[u]);
+#pragma unroll
+                for (int r = 0; r < S; r++) {                                      // fixed order: deterministic
+                    const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
+                    sum[u].x += x.x; sum[u].y += x.y; sum[u].z += x.z; sum[u].w += x.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+            if (ok[u]) epilogue_finish(p, mm[u], nn[u], sum[u], aux[u]);
+    }
+}
+
+// Block- or cluster-wide rendezvous used by every warp role at the same two points of the kernel.
+template <bool kCluster> __device__ __forceinline__ void role_sync() {
+    if (kCluster) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        asm volatile("bar.sync 0;" ::: "memory");
+    }
+}
+
+template <int BN, int S, int CG>
+__global__ void __launch_bounds__(GemmCfg<BN, CG>::kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kEpiWarps = Cfg::kEpiWarps;
     constexpr int kColsPerWarp = 128;                       // accumulator columns held in registers by one epilogue thread
+    constexpr int kEpiThreads = BN >= 256 ? 32 * kEpiWarps : Cfg::kThreads;   // threads sharing the cooperative epilogue
+    constexpr int kBRows = Cfg::kBRows;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms (TMA and UMMA must agree on address bits 7..9)
     unsigned char* data = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]
+    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]   (CG = 2: full and acc_empty are used in the leader only)
     uint64_t* bars = reinterpret_cast<uint64_t*>(data + Cfg::kDataBytes);
     uint64_t* bar_full = bars;
     uint64_t* bar_empty = bars + kStages;
@@ -226,8 +337,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    const int rank = S > 1 ? (int) blockIdx.z : 0;
+    const int pair_rank = CG == 2 ? (int) (blockIdx.x & 1) : 0;                   // 0 = leader of the CTA pair
+    const int n0 = (CG == 2 ? (int) (blockIdx.x >> 1) : (int) blockIdx.x) * BN;   // first output column of the tile
+    const int m0 = (CG == 2 ? (int) blockIdx.y * 2 + pair_rank : (int) blockIdx.y) * BM;
+    const int b_row0 = n0 + pair_rank * kBRows;                                   // first row of B this CTA stages
+    const int rank = S > 1 ? (int) blockIdx.z : 0;                                // split-K index
+    const uint32_t my_cta = (CG == 2 || S > 1) ? cluster_ctarank() : 0u;
+    const uint32_t leader_cta = my_cta & ~1u;
     const int kb_total = (p.K + BK - 1) / BK;
     const int kb0 = (int) ((long long) kb_total * rank / S), kb1 = (int) ((long long) kb_total * (rank + 1) / S);
     const int num_kb = kb1 - kb0;
@@ -238,21 +354,27 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     if (warp == kEpiWarps && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
         for (int s = 0; s < kStages; s++) {
-            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_full[s]), CG);                  // leader's arrive.expect_tx (+ the peer's remote arrive)
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(smem_u32(&bar_acc_full[b]), 1);
-            mbar_init(smem_u32(&bar_acc_empty[b]), kEpiWarps);    // one arrival per epilogue warp
+            mbar_init(smem_u32(&bar_acc_empty[b]), CG * kEpiWarps);   // one arrival per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cg::this_cluster().sync();                 // the peer arrives on the leader's barriers: they must exist first
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                                             // everything below reads what earlier kernels wrote
@@ -261,38 +383,54 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         // ===== producer / MMA warpgroup: needs few registers =====
         if (BN >= 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
         if (warp == kEpiWarps) {
-            // ----- TMA producer -----
+            // ----- TMA producer (every CTA stages its own operand rows) -----
             if (lane == 0) {
                 for (int i = 0; i < num_kb; i++) {
                     const int s = i % kStages;
                     const uint32_t ph = (uint32_t) (i / kStages) & 1u;
-                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free (in both CTAs of a pair)
                     const uint32_t full = smem_u32(&bar_full[s]);
                     if (p.dry & 4) {                                              // experiments: no TMA traffic
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+                        if (CG == 2 && pair_rank == 1) mbar_arrive_cluster(map_to_cta(full, leader_cta));
+                        else if (CG == 2) mbar_expect_tx(full, 0);
+                        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
                         continue;
                     }
-                    mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
                     const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
                     const int kc = (kb0 + i) * BK;
-                    tma_load_2d(base, &tm_a_hi, full, kc, m0);
-                    tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
+                    if (CG == 2) {
+                        const uint32_t full_leader = map_to_cta(full, leader_cta);
+                        if (pair_rank == 0) mbar_expect_tx(full, (uint32_t) (2 * Cfg::kStageBytes));   // both CTAs' bytes land here
+                        else mbar_arrive_cluster(full_leader);
+                        tma_load_2d_pair(base, &tm_a_hi, full_leader, kc, m0);
+                        tma_load_2d_pair(base + BM * BK * 4, &tm_a_lo, full_leader, kc, m0);
 #pragma unroll
-                    for (int h = 0; h < BN / 128; h++) {                          // TMA boxes are at most 256 rows; use 128-row boxes
-                        tma_load_2d(base + 2 * BM * BK * 4 + h * 128 * BK * 4, &tm_b_hi, full, kc, n0 + h * 128);
-                        tma_load_2d(base + 2 * BM * BK * 4 + BN * BK * 4 + h * 128 * BK * 4, &tm_b_lo, full, kc, n0 + h * 128);
+                        for (int h = 0; h < kBRows / 128; h++) {
+                            tma_load_2d_pair(base + 2 * BM * BK * 4 + h * 128 * BK * 4, &tm_b_hi, full_leader, kc, b_row0 + h * 128);
+                            tma_load_2d_pair(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * 128 * BK * 4, &tm_b_lo, full_leader, kc, b_row0 + h * 128);
+                        }
+                    } else {
+                        mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
+                        tma_load_2d(base, &tm_a_hi, full, kc, m0);
+                        tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
+#pragma unroll
+                        for (int h = 0; h < kBRows / 128; h++) {                  // TMA boxes are at most 256 rows; use 128-row boxes
+                            tma_load_2d(base + 2 * BM * BK * 4 + h * 128 * BK * 4, &tm_b_hi, full, kc, b_row0 + h * 128);
+                            tma_load_2d(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * 128 * BK * 4, &tm_b_lo, full, kc, b_row0 + h * 128);
+                        }
                     }
                 }
             }
-        } else if (warp == kEpiWarps + 1) {
-            // ----- MMA issuer (one thread).  Chunk c accumulates into TMEM buffer c & 1. -----
+        } else if (warp == kEpiWarps + 1 && pair_rank == 0) {
+            // ----- MMA issuer (one thread of the leader CTA).  Chunk c accumulates into TMEM buffer c & 1. -----
             if (lane == 0) {
-                constexpr uint32_t idesc = umma_idesc_tf32(BN);
+                constexpr uint32_t idesc = umma_idesc_tf32_mn(BM * CG, BN);
+                const uint16_t pair_mask = (uint16_t) (3u << leader_cta);          // both CTAs of this pair
                 int i = 0;
                 for (int c = 0; c < num_chunks; c++) {
                     const int buf = c & 1;
                     const uint32_t use = (uint32_t) (c >> 1);
-                    mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);    // epilogue drained this buffer
+                    mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);    // epilogue warps (of both CTAs) drained this buffer
                     tcgen05_fence_after();
                     const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * BN);
                     const int i_end = min(num_kb, (c + 1) * kChunk);
@@ -300,28 +438,42 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     for (; i < i_end; i++) {
                         const int s = i % kStages;
                         const uint32_t ph = (uint32_t) (i / kStages) & 1u;
-                        mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed
+                        mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed (both CTAs)
                         tcgen05_fence_after();
                         const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
                         const uint32_t a_hi = base, a_lo = base + BM * BK * 4;
-                        const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + BN * BK * 4;
+                        const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + kBRows * BK * 4;
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; kk++) {
                             if (p.dry & 2) break;                                  // experiments: no tensor-core work
                             const uint32_t off = kk * UMMA_K * 4;                  // 32 bytes along K inside the swizzle span
                             const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
                             const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
-                            umma_tf32(tmem_acc, dal, dbh, idesc, first ? 0u : 1u); // small terms first
-                            umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
-                            umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                            if (CG == 2) {
+                                umma_tf32_pair(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);   // small terms first
+                                umma_tf32_pair(tmem_acc, dah, dbl, idesc, 1u);
+                                umma_tf32_pair(tmem_acc, dah, dbh, idesc, 1u);
+                            } else {
+                                umma_tf32(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);
+                                umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+                                umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                            }
                             first = false;
                         }
-                        umma_commit(smem_u32(&bar_empty[s]));                      // frees the slot when these MMAs retire
+                        if (CG == 2) umma_commit_pair(smem_u32(&bar_empty[s]), pair_mask);   // frees the slot in both CTAs
+                        else umma_commit(smem_u32(&bar_empty[s]));
                     }
-                    umma_commit(smem_u32(&bar_acc_full[buf]));                     // chunk complete
+                    if (CG == 2) umma_commit_pair(smem_u32(&bar_acc_full[buf]), pair_mask);   // chunk complete, both CTAs' epilogues
+                    else umma_commit(smem_u32(&bar_acc_full[buf]));
                 }
             }
         }
+        role_sync<(S > 1)>();
+        // BN = 128: these warps are idle by now and keep their registers: they take a share of the epilogue.
+        // BN = 256: they gave their registers to the epilogue warps (setmaxnreg) and only keep the rendezvous.
+        if (BN < 256 && !(p.dry & 8))
+            cooperative_epilogue<BN, S, CG, Cfg::kThreads>(p, data, rank, pair_rank, m0, n0, (int) threadIdx.x);
+        role_sync<(S > 1 || CG == 2)>();
     } else {
         // ===== epilogue warps: promote TMEM chunks into fp32 registers (round-to-nearest adds) =====
         if (BN >= 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
@@ -338,6 +490,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             tcgen05_fence_after();
 #pragma unroll
             for (int cc = 0; cc < kColsPerWarp / 32; cc++) {
+                if (p.dry & 16) break;                                             // experiments: no TMEM drain
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (buf * BN + col0 + cc * 32), r);
 #pragma unroll
@@ -345,59 +498,31 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_acc_empty[buf])) : "memory");
-        }
-        if (S == 1) {
-            const int m = m0 + row;
-            if (m < p.M) {
-#pragma unroll
-                for (int j = 0; j < kColsPerWarp; j += 4) {
-                    const int n = n0 + col0 + j;
-                    if (n < p.N) epilogue_store4(p, m, n, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
-                }
+            if (lane == 0) {
+                const uint32_t bar = smem_u32(&bar_acc_empty[buf]);
+                if (CG == 2) mbar_arrive_cluster(map_to_cta(bar, leader_cta));     // the MMA issuer lives in the leader
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
             }
-        } else {
-            // park the partial tile (all TMA loads have landed and been consumed: the stage buffers are free)
+        }
+        {
+            // park the tile in shared memory (all TMA loads have landed and been consumed: the stage buffers are free).
+            // Unsplit GEMMs do this too: the epilogue below then walks ROWS with consecutive lanes, i.e. 512-byte coalesced
+            // global stores, instead of every lane writing 16 bytes into a different row (measured: 47 -> 27 us on the
+            // 1024 x 4500 x 512 force GEMM).
             float* dst = reinterpret_cast<float*>(data) + (size_t) row * Cfg::kStagingLd + col0;
 #pragma unroll
             for (int j = 0; j < kColsPerWarp; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
+        role_sync<(S > 1)>();                                                      // every partial tile (of the split) is parked
+        if (!(p.dry & 8)) cooperative_epilogue<BN, S, CG, kEpiThreads>(p, data, rank, pair_rank, m0, n0, (int) threadIdx.x);
+        role_sync<(S > 1 || CG == 2)>();                                           // nobody leaves while peers still read / share TMEM
     }
 
-    if (S > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cluster.sync();                                                            // every partial tile is parked
-        // BN = 128: every thread of the CTA takes part (the producer / MMA / spare warps are idle by now);
-        // BN = 256: only the epilogue warps (the other warpgroup gave its registers away with setmaxnreg)
-        constexpr int kReduceThreads = BN >= 256 ? 32 * kEpiWarps : Cfg::kThreads;
-        if ((int) threadIdx.x < kReduceThreads) {
-            constexpr int kRows = BM / S;                                          // rows this CTA reduces
-            constexpr int kVecPerRow = BN / 4;
-            const int t = threadIdx.x;
-            float* staging = reinterpret_cast<float*>(data);
-            const float* peer[S];
-#pragma unroll
-            for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, r);
-            for (int v = t; v < kRows * kVecPerRow; v += kReduceThreads) {
-                const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
-                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int r = 0; r < S; r++) {                                      // fixed order: deterministic
-                    const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
-                    sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
-                }
-                const int m = m0 + row, n = n0 + col;
-                if (m < p.M && n < p.N) epilogue_store4(p, m, n, sum);
-            }
-        }
-        cluster.sync();                                                            // nobody leaves while peers still read
-    } else {
-        __syncthreads();
-    }
     if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
     }
 }
 
@@ -602,10 +727,20 @@ static bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+
 struct GemmOp {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     GemmParams p;
     char name[48];
+};
+
+constexpr int kPlanSlots = 2;         // independent activation-buffer sets: two chunks of a call may be in flight at once
+
+struct PlanSlot {
+    int cap = 0;                                    // replica capacity of the activation buffers
+    // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as TF32 pairs
+    float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {}, *row_mean = nullptr;
+    std::vector<GemmOp> fwd, bwd;
 };
 
 struct TensorPlan {
@@ -614,20 +749,18 @@ struct TensorPlan {
     int types[kMaxLayers];
     int ld[kMaxLayers];
     int sm_count = 148;
-    int cap = 0;                                    // replica capacity of the activation buffers
     // weights (TF32 pairs), forward [n_{l+1}][ld(n_l)] and transposed [n_l][ld(n_{l+1})], l = 0..L-3
     float *w_hi[kMaxLayers] = {}, *w_lo[kMaxLayers] = {}, *wt_hi[kMaxLayers] = {}, *wt_lo[kMaxLayers] = {}, *bias[kMaxLayers] = {};
-    // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as TF32 pairs; G0 plain
-    float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {}, *row_mean = nullptr;
+    PlanSlot slots[kPlanSlots];
     double* wsum = nullptr;                         // [3][n_1]: sum over atoms of W_0[k][3i+c]
     bool sel_identity = false;                      // selection is atoms 0..A-1 in order
-    int force_bn = 0;                               // ANNF_GEMM_BN=128|256 overrides the tile-width heuristic (experiments)
+    int force_bn = 0;                               // ANNF_GEMM_BN=128|256 (1-CTA tiles) or 512 (CTA pairs) overrides the tile heuristic
     int force_split = 0;                            // ANNF_GEMM_SPLIT_SHORTK=1|2|4|8 overrides split-K for GEMMs with K <= 1024
     int dry = 0;                                    // ANNF_TENSOR_DRY=1: every kernel returns at once (launch-floor measurement)
-    std::vector<GemmOp> fwd, bwd;
+    bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
 };
 
-static void free_activations(TensorPlan* t) {
+static void free_activations(PlanSlot* t) {
     for (int l = 0; l < kMaxLayers; l++) {
         cudaFree(t->x_hi[l]); cudaFree(t->x_lo[l]); cudaFree(t->d_hi[l]); cudaFree(t->d_lo[l]);
         t->x_hi[l] = t->x_lo[l] = t->d_hi[l] = t->d_lo[l] = nullptr;
@@ -639,7 +772,7 @@ static void free_activations(TensorPlan* t) {
 
 void tensor_plan_destroy(TensorPlan* t) {
     if (!t) return;
-    free_activations(t);
+    for (PlanSlot& slot : t->slots) free_activations(&slot);
     for (int l = 0; l < kMaxLayers; l++) {
         cudaFree(t->w_hi[l]); cudaFree(t->w_lo[l]); cudaFree(t->wt_hi[l]); cudaFree(t->wt_lo[l]); cudaFree(t->bias[l]);
     }
@@ -732,11 +865,11 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     return t;
 }
 
-static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
+static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView& net, int R) {
     if (R <= t->cap) return cudaSuccess;
     free_activations(t);
     const int cap = round_up(R, BM);
-    const int L = t->L;
+    const int L = plan->L;
     auto alloc = [&](float** p, int ld) {
         cudaError_t e = cudaMalloc((void**) p, sizeof(float) * (size_t) cap * ld);
         if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(float) * (size_t) cap * ld);
@@ -744,10 +877,10 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
     };
     cudaError_t err = cudaSuccess;
     for (int l = 0; l + 1 < L && err == cudaSuccess; l++) {
-        err = alloc(&t->x_hi[l], t->ld[l]);
-        if (err == cudaSuccess) err = alloc(&t->x_lo[l], t->ld[l]);
-        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_hi[l], t->ld[l]);
-        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], t->ld[l]);
+        err = alloc(&t->x_hi[l], plan->ld[l]);
+        if (err == cudaSuccess) err = alloc(&t->x_lo[l], plan->ld[l]);
+        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_hi[l], plan->ld[l]);
+        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], plan->ld[l]);
     }
     if (err == cudaSuccess) err = alloc(&t->row_mean, 4);
     if (err != cudaSuccess) return err;
@@ -757,23 +890,23 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
     for (int l = 0; l + 2 < L; l++) {                 // forward: X_{l+1} = act(X_l W_l^T + b)
         GemmOp op;
         memset(&op, 0, sizeof(op));
-        const int K = t->nodes[l], N = t->nodes[l + 1];
-        bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, t->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, t->ld[l], BM) &&
-                  make_map(&op.b_hi, t->w_hi[l], N, K, t->ld[l], 128) && make_map(&op.b_lo, t->w_lo[l], N, K, t->ld[l], 128);
+        const int K = plan->nodes[l], N = plan->nodes[l + 1];
+        bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, plan->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, plan->ld[l], BM) &&
+                  make_map(&op.b_hi, plan->w_hi[l], N, K, plan->ld[l], 128) && make_map(&op.b_lo, plan->w_lo[l], N, K, plan->ld[l], 128);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
-        op.p.epi = t->types[l] == ANNF_TANH ? EPI_BIAS_TANH : EPI_BIAS_LINEAR;
+        op.p.epi = plan->types[l] == ANNF_TANH ? EPI_BIAS_TANH : EPI_BIAS_LINEAR;
         op.p.bias = net.b32 + net.b_off[l];
-        op.p.out_hi = t->x_hi[l + 1]; op.p.out_lo = t->x_lo[l + 1]; op.p.ld_out = t->ld[l + 1];
+        op.p.out_hi = t->x_hi[l + 1]; op.p.out_lo = t->x_lo[l + 1]; op.p.ld_out = plan->ld[l + 1];
         snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] fwd%d tf32x3", N, K, l);
         t->fwd.push_back(op);
     }
     for (int l = L - 3; l >= 0; l--) {                // backward: D_l = (D_{l+1} W_l) (.) act'(X_l);  l = 0 -> G0
         GemmOp op;
         memset(&op, 0, sizeof(op));
-        const int K = t->nodes[l + 1], N = t->nodes[l];
-        bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, t->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, t->ld[l + 1], BM) &&
-                  make_map(&op.b_hi, t->wt_hi[l], N, K, t->ld[l + 1], 128) && make_map(&op.b_lo, t->wt_lo[l], N, K, t->ld[l + 1], 128);
+        const int K = plan->nodes[l + 1], N = plan->nodes[l];
+        bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM) &&
+                  make_map(&op.b_hi, plan->wt_hi[l], N, K, plan->ld[l + 1], 128) && make_map(&op.b_lo, plan->wt_lo[l], N, K, plan->ld[l + 1], 128);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
         if (l == 0) {
@@ -781,9 +914,9 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
             op.p.row_mean = t->row_mean;
             op.p.neg_inv_scale = (float) (-1.0 / net.scale);
         } else {
-            op.p.epi = t->types[l - 1] == ANNF_TANH ? EPI_TANH_GRAD : EPI_LINEAR_GRAD;
-            op.p.aux_hi = t->x_hi[l]; op.p.aux_lo = t->x_lo[l]; op.p.ld_aux = t->ld[l];
-            op.p.out_hi = t->d_hi[l]; op.p.out_lo = t->d_lo[l]; op.p.ld_out = t->ld[l];
+            op.p.epi = plan->types[l - 1] == ANNF_TANH ? EPI_TANH_GRAD : EPI_LINEAR_GRAD;
+            op.p.aux_hi = t->x_hi[l]; op.p.aux_lo = t->x_lo[l]; op.p.ld_aux = plan->ld[l];
+            op.p.out_hi = t->d_hi[l]; op.p.out_lo = t->d_lo[l]; op.p.ld_out = plan->ld[l];
         }
         snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] bwd%d tf32x3", N, K, l);
         t->bwd.push_back(op);
@@ -793,8 +926,8 @@ static cudaError_t ensure_capacity(TensorPlan* t, const NetView& net, int R) {
 
 // Launch with programmatic dependent launch allowed (and, for the GEMM, its split-K cluster shape).
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_z,
-                              Args&&... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              int cluster_z, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -807,7 +940,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     n++;
     if (cluster_z > 0) {
         attr[n].id = cudaLaunchAttributeClusterDimension;
-        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.x = cluster_x;
         attr[n].val.clusterDim.y = 1;
         attr[n].val.clusterDim.z = cluster_z;
         n++;
@@ -817,18 +950,24 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int BN, int S>
+template <int BN, int S, int CG>
 static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, CG>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
+        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (err != cudaSuccess) return err;
+        if (CG * S > 8) {
+            err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (err != cudaSuccess) return err;
+        }
         configured[dev] = true;
     }
-    return launch_pdl(gemm3x_kernel<BN, S>, dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, S), dim3(GemmCfg<BN>::kThreads),
-                      GemmCfg<BN>::kSmemBytes, stream, S, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p);
+    const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM * CG - 1) / (BM * CG);
+    return launch_pdl(gemm3x_kernel<BN, S, CG>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG, S,
+                      op.a_hi, op.a_lo, op.b_hi, op.b_lo, p);
 }
 
 static int pick_split(int tiles, int k_blocks, int sm_count) {
@@ -848,36 +987,64 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         const bool vec_ok = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(forces) & 15) == 0;
         p.sel_atoms = vec_ok ? nullptr : net.sel_atoms;
     }
-    // 256-wide tiles move 25% fewer operand bytes per flop and halve the CTA count (one wave instead of two for
-    // the 4500-wide backward GEMM: 59.8 -> 48.2 us measured), but their 2-stage pipeline and 8-way split-K reduce
-    // lose on GEMMs that need split-K to fill the machine (fwd 1024x512x4500: 41 -> 74 us).  So: 256 only when the
-    // 128-wide tiling would already fill the SMs without splitting K.
-    const int tiles128 = ((p.N + 127) / 128) * ((R + BM - 1) / BM);
-    int bn = tiles128 > t->sm_count ? 256 : 128;
-    if (t->force_bn == 128 || t->force_bn == 256) bn = t->force_bn;
+    // Tile shape.  CTA pairs (cta_group::2, 256 x 256 tiles): each SM stages 128 rows of A and HALF of the B tile and the MMA
+    // reads 25% fewer shared-memory bytes per flop — the two things the 1-CTA kernel is bound by.  They need
+    // enough work to fill the machine with 256 x 256 tiles (possibly split along K); small GEMMs stay on 128 x 128 tiles.
+    const int kb = (p.K + BK - 1) / BK;
+    int mode = t->force_bn;                                     // 0 auto, 128 / 256: 1-CTA tiles, 512: CTA pairs
+    if (mode == 0) {
+        const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);
+        const int s2 = pick_split(pair_ctas, kb, t->sm_count);
+        const int tiles128 = ((p.N + 127) / 128) * ((R + BM - 1) / BM);
+        // measured at BASELINE C5 (1024 replicas): the unsplit 1024x4500x512 force GEMM runs 45.0 / 38.5 / 37.3 us with
+        // 128-wide / 256-wide / CTA-pair tiles; the split-K 1024x512x4500 GEMM 41.5 / 72 / 78 us (2x8 clusters and an
+        // 8-way DSMEM reduce of 128 KB partials lose).  So: CTA pairs when they fill the machine WITHOUT splitting K.
+        if (p.N >= 256 && s2 == 1 && pair_ctas >= t->sm_count / 2) mode = 512;
+        else mode = (tiles128 > t->sm_count && pick_split(tiles128, kb, t->sm_count) == 1) ? 256 : 128;
+    }
+    if (mode == 512) {
+        const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);
+        int s = pick_split(pair_ctas, kb, t->sm_count);
+        if (t->force_split > 0 && kb <= 32) s = t->force_split;
+        if (s == 8 && !t->no_cluster16) {
+            // 2 x 8 = 16 CTAs is a non-portable cluster size: if this device cannot co-schedule it, remember and use 2 x 4
+            const cudaError_t e = launch_gemm_t<256, 8, 2>(op, p, stream);
+            if (e == cudaSuccess) return e;
+            cudaGetLastError();
+            t->no_cluster16 = true;
+        }
+        if (s == 8) s = 4;
+        switch (s) {
+        case 4: return launch_gemm_t<256, 4, 2>(op, p, stream);
+        case 2: return launch_gemm_t<256, 2, 2>(op, p, stream);
+        default: return launch_gemm_t<256, 1, 2>(op, p, stream);
+        }
+    }
+    const int bn = mode == 256 ? 256 : 128;
     const int tiles = ((p.N + bn - 1) / bn) * ((R + BM - 1) / BM);
-    int s = pick_split(tiles, (p.K + BK - 1) / BK, t->sm_count);
-    if (t->force_split > 0 && (p.K + BK - 1) / BK <= 32) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
+    int s = pick_split(tiles, kb, t->sm_count);
+    if (t->force_split > 0 && kb <= 32) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
     if (bn == 256) {
         switch (s) {
-        case 8: return launch_gemm_t<256, 8>(op, p, stream);
-        case 4: return launch_gemm_t<256, 4>(op, p, stream);
-        case 2: return launch_gemm_t<256, 2>(op, p, stream);
-        default: return launch_gemm_t<256, 1>(op, p, stream);
+        case 8: return launch_gemm_t<256, 8, 1>(op, p, stream);
+        case 4: return launch_gemm_t<256, 4, 1>(op, p, stream);
+        case 2: return launch_gemm_t<256, 2, 1>(op, p, stream);
+        default: return launch_gemm_t<256, 1, 1>(op, p, stream);
         }
     }
     switch (s) {
-    case 8: return launch_gemm_t<128, 8>(op, p, stream);
-    case 4: return launch_gemm_t<128, 4>(op, p, stream);
-    case 2: return launch_gemm_t<128, 2>(op, p, stream);
-    default: return launch_gemm_t<128, 1>(op, p, stream);
+    case 8: return launch_gemm_t<128, 8, 1>(op, p, stream);
+    case 4: return launch_gemm_t<128, 4, 1>(op, p, stream);
+    case 2: return launch_gemm_t<128, 2, 1>(op, p, stream);
+    default: return launch_gemm_t<128, 1, 1>(op, p, stream);
     }
 }
 
 cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, int R, const float* coords,
                             int atoms_per_replica, const float* centers, float* forces, double* energies,
-                            cudaStream_t stream, long long* launches) {
-    cudaError_t err = ensure_capacity(t, net, R);
+                            cudaStream_t stream, long long* launches, int slot_index) {
+    PlanSlot* sl = &t->slots[slot_index % kPlanSlots];
+    cudaError_t err = ensure_capacity(t, sl, net, R);
     if (err != cudaSuccess) return err;
     const int L = t->L;
     char name[64];
@@ -891,25 +1058,25 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
     err = timed("prep_kernel", [&] {
         const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
                                (t->dry ? 2 : 0);
-        return launch_pdl(prep_kernel, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 0, net, R, coords, atoms_per_replica,
-                          t->x_hi[0], t->x_lo[0], t->ld[0], contiguous);
+        return launch_pdl(prep_kernel, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
+                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous);
     });
     if (err != cudaSuccess) return err;
-    for (const GemmOp& op : t->fwd) {
+    for (const GemmOp& op : sl->fwd) {
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
         err = timed(name, [&] { return launch_gemm(t, op, R, stream, net, nullptr, 0); });
         if (err != cudaSuccess) return err;
     }
     err = timed("head_kernel", [&] {
-        return launch_pdl(head_kernel, dim3(R), dim3(kHeadThreads), 0, stream, 0, net, t->dry ? -R : R, centers, (const float*) t->x_hi[L - 2],
-                          (const float*) t->x_lo[L - 2], t->ld[L - 2], t->d_hi[L - 2], t->d_lo[L - 2], energies);
+        return launch_pdl(head_kernel, dim3(R), dim3(kHeadThreads), 0, stream, 1, 0, net, t->dry ? -R : R, centers, (const float*) sl->x_hi[L - 2],
+                          (const float*) sl->x_lo[L - 2], t->ld[L - 2], sl->d_hi[L - 2], sl->d_lo[L - 2], energies);
     });
     if (err != cudaSuccess) return err;
-    for (const GemmOp& op : t->bwd) {
+    for (const GemmOp& op : sl->bwd) {
         if (op.p.epi == EPI_FORCE) {
             err = timed("colmean_kernel", [&] {
-                return launch_pdl(colmean_kernel, dim3(R), dim3(128), 0, stream, 0, t->dry ? -R : R, t->nodes[1], net.n_sel, (const float*) t->d_hi[1],
-                                  (const float*) t->d_lo[1], t->ld[1], (const double*) t->wsum, t->row_mean);
+                return launch_pdl(colmean_kernel, dim3(R), dim3(128), 0, stream, 1, 0, t->dry ? -R : R, t->nodes[1], net.n_sel, (const float*) sl->d_hi[1],
+                                  (const float*) sl->d_lo[1], t->ld[1], (const double*) t->wsum, sl->row_mean);
             });
             if (err != cudaSuccess) return err;
         }

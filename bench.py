@@ -93,6 +93,8 @@ class ClockSampler:
             self._stop.wait(0.01)
 
     def start(self):
+        if os.environ.get("BENCH_NO_CLOCK_THREAD"):      # experiments: main-thread samples only
+            return
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 

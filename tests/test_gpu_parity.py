@@ -254,6 +254,7 @@ def test_wide_network_properties_and_sampled_parity():
     ([600, 512, 128, 4], ["Tanh", "Tanh", "Tanh"], 64),          # split-K 4 (19 and 16 K-blocks), no split backward
     ([300, 128, 4], ["Tanh", "Softmax"], 1),                     # one hidden layer, single replica, Softmax head
     ([1536, 256, 256, 2], ["Tanh", "Tanh", "Linear"], 384),      # three M tiles
+    ([4500, 512, 512, 8], ["Tanh", "Tanh", "Tanh"], 600),        # BASELINE C5 widths: CTA-pair GEMMs, 2 x 8 clusters, ragged M
 ])
 def test_tensor_core_path_matches_oracle(nodes, types, R):
     """tcgen05 3xTF32 path.  Stated tolerance (BASELINE config 5 "tensor-core dense-contraction path, stated
@@ -278,10 +279,11 @@ def test_tensor_core_path_matches_oracle(nodes, types, R):
     np.testing.assert_array_equal(f, f2)
 
 
-@pytest.mark.parametrize("bn", ["128", "256"])
+@pytest.mark.parametrize("bn", ["128", "256", "512"])
 def test_tensor_core_tile_widths_agree(bn, monkeypatch):
-    """Both GEMM tile widths (128: 4 epilogue warps; 256: 8 epilogue warps + setmaxnreg) against the oracle,
-    with split-K 4 and 8, ragged N (600 = 2*256 + 88) and ragged K."""
+    """Every GEMM tile shape against the oracle — 128 wide (4 epilogue warps), 256 wide (8 epilogue warps + setmaxnreg)
+    and "512" = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, multicast commits) — with split-K 4 and 8,
+    ragged N (600 = 2*256 + 88), ragged K and an odd number of 128-row M tiles."""
     monkeypatch.setenv("ANNF_GEMM_BN", bn)
     nodes, types, R = [1200, 600, 320, 6], ["Tanh", "Tanh", "Tanh"], 150
     force = synthetic.make_force(nodes, types, 400, seed=51)
