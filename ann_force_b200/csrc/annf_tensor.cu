@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     pdl_wait();
     if (R < 0) return;                                      // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r_index = r;
     const int L = net.L, nH = net.nodes[L - 2], nL = net.nodes[L - 1];
     __shared__ double part[4][kHeadMaxOut];
     __shared__ double zs[kHeadMaxOut], dzs[kHeadMaxOut], cen[kHeadMaxOut];
@@ -619,13 +620,27 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     const double* b = net.b64 + net.b_off[L - 2];
     const float* ah = a_hi + (size_t) r * ld;
     const float* al = a_lo + (size_t) r * ld;
+    // The loop is bound by global-load latency unless many loads are in flight: four hidden units per thread per pass, their
+    // activations and 4 x 8 weights all loaded before the 32 dependent fp64 FMAs.
     for (int j0 = 0; j0 < nL; j0 += 8) {                    // 8 outputs at a time: 8 independent accumulators per thread
         double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int m = tid; m < nH; m += kHeadThreads) {
-            const double a = (double) (__ldg(ah + m) + __ldg(al + m));   // hi + lo is exact in fp32
+        for (int mb = tid; mb < nH; mb += 4 * kHeadThreads) {
+            float ahv[4], alv[4];
+            double w[4][8];
 #pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (j0 + u < nL) acc[u] = fma(__ldg(W + (size_t) (j0 + u) * nH + m), a, acc[u]);
+            for (int v = 0; v < 4; v++) {
+                const int m = mb + v * kHeadThreads;
+                ahv[v] = m < nH ? __ldg(ah + m) : 0.f;
+                alv[v] = m < nH ? __ldg(al + m) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[v][u] = (m < nH && j0 + u < nL) ? __ldg(W + (size_t) (j0 + u) * nH + m) : 0.0;
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const double a = (double) (ahv[v] + alv[v]);                     // hi + lo is exact in fp32
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = fma(w[v][u], a, acc[u]);
+            }
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -649,17 +664,35 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     if (tid < nL) dzf[tid] = (float) dzs[tid];
     __syncthreads();
     const int hidden_type = net.types[L - 3];
-    for (int m = tid; m < nH; m += kHeadThreads) {          // the result is re-split to TF32 pairs: fp32 FMA is enough here
-        float acc = 0.f;
-        for (int j = 0; j < nL; j++) acc = fmaf(__ldg(W32 + (size_t) j * nH + m), dzf[j], acc);
-        if (hidden_type == ANNF_TANH) {
-            const float a = __ldg(ah + m) + __ldg(al + m);
-            acc *= (1.f - a * a);
+    // the result is re-split to TF32 pairs: fp32 FMA is enough here.  Same batching: 4 hidden units per pass, loads first.
+    for (int mb = tid; mb < nH; mb += 4 * kHeadThreads) {
+        float av[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int m = mb + v * kHeadThreads;
+            av[v] = m < nH ? __ldg(ah + m) + __ldg(al + m) : 0.f;
         }
-        float hi, lo;
-        split_tf32(acc, hi, lo);
-        d_hi[(size_t) r * ld + m] = hi;
-        d_lo[(size_t) r * ld + m] = lo;
+        for (int j = 0; j < nL; j++) {
+            float w[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const int m = mb + v * kHeadThreads;
+                w[v] = m < nH ? __ldg(W32 + (size_t) j * nH + m) : 0.f;
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[v] = fmaf(w[v], dzf[j], acc[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int m = mb + v * kHeadThreads;
+            if (m >= nH) continue;
+            float r = acc[v];
+            if (hidden_type == ANNF_TANH) r *= (1.f - av[v] * av[v]);
+            float hi, lo;
+            split_tf32(r, hi, lo);
+            d_hi[(size_t) r_index * ld + m] = hi;
+            d_lo[(size_t) r_index * ld + m] = lo;
+        }
     }
 }
 
@@ -676,11 +709,26 @@ __global__ void __launch_bounds__(128) colmean_kernel(int R, int K, int A, const
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double part[4][3];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int k = tid; k < K; k += 128) {
-        const double d = (double) (__ldg(d_hi + (size_t) r * ld + k) + __ldg(d_lo + (size_t) r * ld + k));
-        s0 = fma(d, __ldg(wsum + k), s0);
-        s1 = fma(d, __ldg(wsum + K + k), s1);
-        s2 = fma(d, __ldg(wsum + 2 * K + k), s2);
+    for (int kb = tid; kb < K; kb += 4 * 128) {             // four terms per pass, every load issued before the math
+        float dh[4], dl[4];
+        double w0[4], w1[4], w2[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int k = kb + v * 128;
+            const bool in = k < K;
+            dh[v] = in ? __ldg(d_hi + (size_t) r * ld + k) : 0.f;
+            dl[v] = in ? __ldg(d_lo + (size_t) r * ld + k) : 0.f;
+            w0[v] = in ? __ldg(wsum + k) : 0.0;
+            w1[v] = in ? __ldg(wsum + K + k) : 0.0;
+            w2[v] = in ? __ldg(wsum + 2 * K + k) : 0.0;
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const double d = (double) (dh[v] + dl[v]);
+            s0 = fma(d, w0[v], s0);
+            s1 = fma(d, w1[v], s1);
+            s2 = fma(d, w2[v], s2);
+        }
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; }
