@@ -463,7 +463,9 @@ annf_status annf_eval_openmm(annf_handle h, const void* posq, const void* posq_c
 
 annf_status annf_eval_batched(annf_handle h, int32_t R, const float* coords, int32_t atoms_per_replica,
                               const float* centers, float* forces, double* energies, void* stream) {
-    if (!h || !coords || !forces || !energies) return fail(ANNF_ERR_INVALID, "annf_eval_batched: NULL argument");
+    if (!h) return fail(ANNF_ERR_INVALID, "annf_eval_batched: NULL handle");
+    if (R == 0) return ANNF_OK;                                    // an empty batch is a no-op (its buffers may be NULL)
+    if (!coords || !forces || !energies) return fail(ANNF_ERR_INVALID, "annf_eval_batched: NULL argument");
     if (R < 0) return fail(ANNF_ERR_INVALID, "annf_eval_batched: num_replicas = %d", R);
     if (atoms_per_replica < h->num_system_atoms)
         return fail(ANNF_ERR_INVALID, "annf_eval_batched: atoms_per_replica %d < %d system atoms", atoms_per_replica, h->num_system_atoms);
@@ -488,8 +490,10 @@ annf_status annf_eval_batched(annf_handle h, int32_t R, const float* coords, int
 
 annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords_host, int32_t atoms_per_replica,
                                    const float* centers_host, float* forces_host, double* energies_host) {
-    if (!h || !coords_host || !forces_host || !energies_host) return fail(ANNF_ERR_INVALID, "annf_eval_batched_host: NULL argument");
-    if (R <= 0) return R == 0 ? ANNF_OK : fail(ANNF_ERR_INVALID, "annf_eval_batched_host: num_replicas = %d", R);
+    if (!h) return fail(ANNF_ERR_INVALID, "annf_eval_batched_host: NULL handle");
+    if (R == 0) return ANNF_OK;
+    if (!coords_host || !forces_host || !energies_host) return fail(ANNF_ERR_INVALID, "annf_eval_batched_host: NULL argument");
+    if (R < 0) return fail(ANNF_ERR_INVALID, "annf_eval_batched_host: num_replicas = %d", R);
     DeviceGuard guard(h->device);
     const size_t n_coords = (size_t) R * atoms_per_replica * 3, n_centers = (size_t) R * h->net.num_center;
     if (n_coords > h->h_cap_coords) {

@@ -387,3 +387,59 @@ def test_other_featurisers_single_and_batched(kind):
     e1_ref, f1_ref = port.evaluate(force, seen)
     assert abs(e1 - e1_ref) <= 1e-11 * abs(e1_ref)
     assert np.abs(f1 - f1_ref).max() <= 1e-10 * np.abs(f1_ref).max() + 2 * FIXED_POINT_ULP
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge cases: empty and very large batches, rows wider than the system
+# ------------------------------------------------------------------------------------------------------
+def test_empty_batch_is_a_no_op():
+    force = synthetic.make_config("c2")
+    kernel = CalcANNForce()
+    kernel.initialize(7, force)
+    coords = torch.zeros(0, 7, 3, device="cuda")
+    e, f = kernel.execute_batched(coords)
+    assert e.numel() == 0 and f.numel() == 0
+    e_h, f_h = kernel.execute_batched_host(np.zeros((0, 7, 3), dtype=np.float32))
+    assert e_h.size == 0 and f_h.size == 0
+
+
+def test_large_replica_count_and_padded_rows():
+    """100,000 umbrella windows in one launch (grid limits, 64-bit indexing), coordinate rows wider than the System
+    (atoms_per_replica > num_system_atoms): sampled parity + every replica finite + unselected rows untouched."""
+    force = synthetic.make_config("c2")
+    R, N = 100_000, 9
+    pos = synthetic.make_positions(N, R, seed=71)
+    cen = synthetic.make_centers(force, R, seed=72)
+    kernel = CalcANNForce()
+    kernel.initialize(7, force)
+    forces = torch.full((R, N, 3), 7.0, dtype=torch.float32, device="cuda")
+    e, f = kernel.execute_batched(torch.as_tensor(pos, device="cuda"), torch.as_tensor(cen, device="cuda"), forces=forces)
+    torch.cuda.synchronize()
+    e, f = e.cpu().numpy(), f.double().cpu().numpy()
+    assert np.all(np.isfinite(e)) and np.all(np.isfinite(f))
+    assert np.all(f[:, 7:, :] == 7.0)                                  # atoms outside the selection keep what was there
+    sample = np.array([0, 1, 4095, 4096, 65535, 65536, 99_999])
+    e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
+    np.testing.assert_allclose(e[sample], e_ref, rtol=1e-11)
+    assert max_norm_rel(f[sample][:, :7], f_ref[:, :7]) <= 1e-6
+
+
+def test_tensor_path_capacity_growth_and_reuse():
+    """The tensor plan re-allocates when a later call brings more replicas, and both activation-buffer sets of the
+    pipelined host entry give the same answer as the device entry."""
+    force = synthetic.make_force([300, 128, 64, 4], ["Tanh", "Tanh", "Tanh"], 100, seed=81)
+    kernel = CalcANNForce(precision="tf32x3")
+    kernel.initialize(100, force)
+    results = []
+    for R in (40, 300, 129):
+        pos = synthetic.make_positions(100, R, seed=R)
+        e, f = kernel.execute_batched(torch.as_tensor(pos, device="cuda"))
+        torch.cuda.synchronize()
+        e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
+        np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=2e-5)
+        assert max_norm_rel(f.double().cpu().numpy(), f_ref) <= F_RTOL
+        results.append((pos, e.cpu().numpy(), f.cpu().numpy()))
+    pos, e_dev, f_dev = results[1]
+    e_h, f_h = kernel.execute_batched_host(pos)
+    np.testing.assert_array_equal(e_h, e_dev)
+    np.testing.assert_array_equal(f_h, f_dev)
