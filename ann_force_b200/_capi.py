@@ -56,6 +56,7 @@ SYMBOLS = {
     "annf_eval_openmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
     "annf_eval_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annf_eval_batched_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annf_debug_single_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "annf_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "annf_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTime), C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
 }

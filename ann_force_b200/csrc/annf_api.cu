@@ -19,6 +19,7 @@ namespace annf {
 // annf_single.cu
 size_t single_smem_bytes(const NetView& net, int cluster_size);
 cudaError_t prepare_single(const NetView& net, int cluster_size);
+cudaError_t read_single_phase_clocks(long long* out16);
 cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq, const void* posq_corr,
                           unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream);
 // annf_batched.cu
@@ -570,6 +571,14 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
     ANNF_CUDA(cudaStreamSynchronize(h->host_stream));
     ANNF_CUDA(cudaStreamSynchronize(h->host_stream2));
     ANNF_CUDA(cudaStreamSynchronize(h->in_stream));
+    return ANNF_OK;
+}
+
+annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16) {
+    if (!h || !clocks16) return fail(ANNF_ERR_INVALID, "annf_debug_single_phases: NULL argument");
+    DeviceGuard guard(h->device);
+    ANNF_CUDA(cudaDeviceSynchronize());
+    ANNF_CUDA(read_single_phase_clocks(reinterpret_cast<long long*>(clocks16)));
     return ANNF_OK;
 }
 

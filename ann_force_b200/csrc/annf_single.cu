@@ -25,6 +25,10 @@ namespace cg = cooperative_groups;
 
 namespace annf {
 
+// Diagnostic: clock64() of thread 0 / CTA 0 at the phase boundaries of the last launch (annf_debug_single_phases).
+__device__ long long g_single_phase_clock[16];
+#define ANNF_PHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_single_phase_clock[i] = clock64(); } while (0)
+
 constexpr int kSingleThreads = 256;
 constexpr int kSingleWarps = kSingleThreads / 32;
 
@@ -66,6 +70,15 @@ __device__ __forceinline__ void publish(cg::cluster_group& cluster, int cl, doub
 __device__ __forceinline__ void cluster_or_block_sync(cg::cluster_group& cluster, int cl) {
     if (cl == 1) __syncthreads();
     else cluster.sync();
+}
+
+// Lanes per output of a small mat-vec: the largest power of two (<= 32) such that all outputs fit in one pass of the CTA
+// and every lane still has a few terms to add.  Few lanes per output = few shuffle rounds, which is what bounds these
+// latency-critical contractions (a 40 x 21 layer took 3,800 cycles with one warp per row and 5 x 2 shuffles per sum).
+__device__ __forceinline__ int lanes_per_output(int n_outputs, int n_terms) {
+    int g = 32;
+    while (g > 1 && (g * n_outputs > kSingleThreads || 4 * g > n_terms)) g >>= 1;
+    return g;
 }
 
 // In-place activation of a full layer held in shared memory (every CTA does this redundantly).
@@ -123,6 +136,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = net.L, total = net.node_off[L];
 
+    ANNF_PHASE(0);
     extern __shared__ __align__(16) double smem[];
     double* a = smem;                 // activations  a[node_off[l] + j]
     double* z = a + total;            // pre-activations
@@ -167,20 +181,34 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     const int n0 = net.nodes[0];
     if (net.input_type == ANNF_INPUT_CARTESIAN) {
         const int A = net.n_sel;
+        const double inv_scale = 1.0 / net.scale;           // x / s as x * (1/s): 1 ulp from the reference's division
         double sx = 0.0, sy = 0.0, sz = 0.0;
         for (int i = tid; i < A; i += kSingleThreads) {
             const double3 p = load_pos(args, net.sel_slots[i]);
-            const double x = p.x / net.scale, y = p.y / net.scale, w = p.z / net.scale;   // :139
+            const double x = p.x * inv_scale, y = p.y * inv_scale, w = p.z * inv_scale;   // :139
             a[3 * i] = x; a[3 * i + 1] = y; a[3 * i + 2] = w;
             sx += x; sy += y; sz += w;
         }
-        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-        if (lane == 0) { red[8 + 3 * warp] = sx; red[8 + 3 * warp + 1] = sy; red[8 + 3 * warp + 2] = sz; }
-        __syncthreads();
-        if (tid < 3) {
-            double s = 0.0;
-            for (int w = 0; w < kSingleWarps; w++) s += red[8 + 3 * w + tid];
-            red[tid] = s / A;                                                             // unweighted centroid :137-141
+        if (A <= 32) {
+            // the whole selection sits in warp 0: three interleaved shuffle reductions, no block-level hop
+            if (warp == 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+                }
+                if (lane == 0) { red[0] = sx / A; red[1] = sy / A; red[2] = sz / A; }   // unweighted centroid :137-141
+            }
+        } else {
+            sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+            if (lane == 0) { red[8 + 3 * warp] = sx; red[8 + 3 * warp + 1] = sy; red[8 + 3 * warp + 2] = sz; }
+            __syncthreads();
+            if (tid < 3) {
+                double t = 0.0;
+                for (int w = 0; w < kSingleWarps; w++) t += red[8 + 3 * w + tid];
+                red[tid] = t / A;
+            }
         }
         __syncthreads();
         for (int i = tid; i < n0; i += kSingleThreads) a[i] -= red[i % 3];                // :143-145
@@ -208,8 +236,10 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
             }
         }
     }
+    ANNF_PHASE(1);                                         // features done (this thread)
     if (cl == 1) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    ANNF_PHASE(2);                                         // weights staged, everyone here
 
     // ---- forward: calculate_output_of_each_layer, ANN_ReferenceKernels.cpp:179-260 -------------
     for (int l = 0; l + 1 < L; l++) {
@@ -220,31 +250,41 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         double* zout = z + net.node_off[l + 1];
         const int per = (n_out + cl - 1) / cl;
         const int j0 = rank * per, j1 = min(n_out, j0 + per);
-        // a warp owns rows j0+warp, +8, +16, +24 (four independent dot products in flight), then +32 ...
-        for (int jb = j0 + warp; jb < j1; jb += 4 * kSingleWarps) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int i = lane; i < n_in; i += 32) {
-                const double x = ain[i];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int j = jb + u * kSingleWarps;
-                    if (j < j1) acc[u] = fma(W[(size_t) j * n_in + i], x, acc[u]);
+        // each output row is shared by G lanes (power of two, inside one warp); all rows of the slice go in as few passes as possible
+        const int G = lanes_per_output(j1 - j0, n_in);
+        const int rows_per_pass = kSingleThreads / G, g = tid & (G - 1), slot = tid / G;
+        const int passes = (max(j1 - j0, 0) + rows_per_pass - 1) / rows_per_pass;
+        for (int pass = 0; pass < passes; pass++) {
+            const int j = j0 + pass * rows_per_pass + slot;
+            const bool valid = j < j1;
+            double acc0 = 0.0, acc1 = 0.0;
+            if (valid) {
+                const double* wrow = W + (size_t) j * n_in;
+                int i = g;
+                for (; i + G < n_in; i += 2 * G) {
+                    acc0 = fma(wrow[i], ain[i], acc0);
+                    acc1 = fma(wrow[i + G], ain[i + G], acc1);
                 }
+                if (i < n_in) acc0 = fma(wrow[i], ain[i], acc0);
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int j = jb + u * kSingleWarps;
-                const double s = warp_sum(acc[u]);
-                if (j < j1) publish(cluster, cl, zout + j, s + b[j], lane);                // :193-198
+            double sum = acc0 + acc1;
+            for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (valid && g == 0) {                                                         // :193-198
+                const double v = sum + b[j];
+                if (cl == 1) zout[j] = v;
+                else for (int r = 0; r < cl; r++) *cluster.map_shared_rank(zout + j, r) = v;
             }
         }
         cluster_or_block_sync(cluster, cl);
+        if (l < 2) ANNF_PHASE(7 + 2 * l);                  // diagnostic: connection l contracted
         if (l + 2 < L) {   // hidden layer: activate the whole vector locally
             activate_layer(net.types[l], n_out, zout, a + net.node_off[l + 1]);
             __syncthreads();
         }
+        if (l < 2) ANNF_PHASE(8 + 2 * l);                  // diagnostic: layer l + 1 activated
     }
 
+    ANNF_PHASE(3);                                         // forward done
     // ---- energy + output-layer gradient (fp64; one output or Circular pair per thread; identical in every CTA) -----
     {
         const int n_last = net.nodes[L - 1];
@@ -261,6 +301,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
     }
     __syncthreads();
 
+    ANNF_PHASE(4);                                         // head done
     // ---- backward: back_prop, ANN_ReferenceKernels.cpp:299-373 ----------------------------------
     for (int l = L - 2; l >= 0; l--) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
@@ -269,23 +310,27 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         double* dout = d + net.node_off[l];
         const int per = (n_in + cl - 1) / cl;
         const int m0 = rank * per, m1 = min(n_in, m0 + per);
-        for (int m = m0 + tid; m < m1; m += kSingleThreads) {
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            int k = 0;
-            for (; k + 4 <= n_out; k += 4) {
-                const double w0 = W[(size_t) (k + 0) * n_in + m], w1 = W[(size_t) (k + 1) * n_in + m];
-                const double w2 = W[(size_t) (k + 2) * n_in + m], w3 = W[(size_t) (k + 3) * n_in + m];
-                acc0 = fma(w0, dz[k + 0], acc0);
-                acc1 = fma(w1, dz[k + 1], acc1);
-                acc2 = fma(w2, dz[k + 2], acc2);
-                acc3 = fma(w3, dz[k + 3], acc3);
+        // column m of W^T * dz is shared by G lanes, each walking rows k = g, g + G, ... (consecutive columns in neighbouring groups)
+        const int G = lanes_per_output(m1 - m0, n_out);
+        const int cols_per_pass = kSingleThreads / G, g = tid & (G - 1), slot = tid / G;
+        const int passes = (max(m1 - m0, 0) + cols_per_pass - 1) / cols_per_pass;
+        for (int pass = 0; pass < passes; pass++) {
+            const int m = m0 + pass * cols_per_pass + slot;
+            const bool valid = m < m1;
+            double acc0 = 0.0, acc1 = 0.0;
+            if (valid) {
+                int k = g;
+                for (; k + G < n_out; k += 2 * G) {
+                    acc0 = fma(W[(size_t) k * n_in + m], dz[k], acc0);
+                    acc1 = fma(W[(size_t) (k + G) * n_in + m], dz[k + G], acc1);
+                }
+                if (k < n_out) acc0 = fma(W[(size_t) k * n_in + m], dz[k], acc0);
             }
-            for (; k < n_out; k++) acc0 = fma(W[(size_t) k * n_in + m], dz[k], acc0);
-            const double v = (acc0 + acc1) + (acc2 + acc3);
-            if (cl == 1) {
-                dout[m] = v;
-            } else {
-                for (int r = 0; r < cl; r++) *cluster.map_shared_rank(dout + m, r) = v;
+            double v = acc0 + acc1;
+            for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (valid && g == 0) {
+                if (cl == 1) dout[m] = v;
+                else for (int r = 0; r < cl; r++) *cluster.map_shared_rank(dout + m, r) = v;
             }
         }
         cluster_or_block_sync(cluster, cl);
@@ -295,25 +340,26 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
         }
     }
 
+    ANNF_PHASE(5);                                         // backward done
     // ---- forces: get_all_forces_from_derivative_of_first_layer, ANN_ReferenceKernels.cpp:397-410 --
     if (!(args.flags & ANNF_FLAG_SKIP_FORCES) && net.input_type == ANNF_INPUT_CARTESIAN) {
         const int A = net.n_sel;
         const double* g = d;   // dE/dx, layer 0
         // mean gradient per component = the Jacobian term of centroid removal (:402-406), O(A) not O(A^2)
         if (warp < 3) {
-            double s = 0.0;
-            for (int i = lane; i < A; i += 32) s += g[3 * i + warp];
-            s = warp_sum(s);
-            if (lane == 0) red[warp] = s / A;
+            double t = 0.0;
+            for (int i = lane; i < A; i += 32) t += g[3 * i + warp];
+            t = warp_sum(t);
+            if (lane == 0) red[warp] = t / A;
         }
         __syncthreads();
         const int per = (A + cl - 1) / cl;
         const int i0 = rank * per, i1 = min(A, i0 + per);
+        const double scale_to_fixed = -(double) 0x100000000LL / net.scale;             // -(1/s) folded into the fixed-point scale
         for (int t = 3 * i0 + tid; t < 3 * i1; t += kSingleThreads) {
             const int i = t / 3, c = t - 3 * i;
-            const double f = -(g[t] - red[c]) / net.scale;
             atomicAdd(&args.force[net.sel_slots[i] + c * args.padded],
-                      (unsigned long long) ((long long) (f * (double) 0x100000000LL)));
+                      (unsigned long long) ((long long) ((g[t] - red[c]) * scale_to_fixed)));
         }
     }
     if (!(args.flags & ANNF_FLAG_SKIP_FORCES) && net.input_type != ANNF_INPUT_CARTESIAN && rank == 0) {
@@ -345,6 +391,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_kernel(const Si
                       (unsigned long long) ((long long) (facc[t] * (double) 0x100000000LL)));
         }
     }
+    ANNF_PHASE(6);                                         // forces issued
     if (rank == 0 && tid == 0 && args.energy != nullptr && !(args.flags & ANNF_FLAG_SKIP_ENERGY)) {
         // fire-and-forget reduction instead of a load + store round trip at the tail of the kernel
         if (args.flags & ANNF_FLAG_ENERGY_DOUBLE) atomicAdd(reinterpret_cast<double*>(args.energy), s_energy);
@@ -356,6 +403,10 @@ static int single_red_doubles(const NetView& net) {
     int max_n = 0;
     for (int l = 0; l < net.L; l++) max_n = net.nodes[l] > max_n ? net.nodes[l] : max_n;
     return 8 + (max_n > 3 * kSingleWarps ? max_n : 3 * kSingleWarps);
+}
+
+cudaError_t read_single_phase_clocks(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_single_phase_clock, sizeof(long long) * 16);
 }
 
 size_t single_smem_bytes(const NetView& net, int cluster_size) {

@@ -152,6 +152,10 @@ ANNF_API annf_status annf_eval_batched_host(annf_handle h, int32_t num_replicas,
                                    int32_t atoms_per_replica, const float* centers_host, float* forces_host,
                                    double* energies_host);
 
+/* Diagnostic: SM clock (clock64) of thread 0 at the phase boundaries of the most recent annf_eval_openmm launch:
+ * [0] start, [1] features, [2] weights staged, [3] forward, [4] energy head, [5] backward, [6] forces issued.  Synchronises. */
+ANNF_API annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16);
+
 /* Per-kernel device timing with CUDA events on the launching stream (for the roofline line). */
 ANNF_API annf_status annf_set_profiling(annf_handle h, int32_t enabled);
 ANNF_API annf_status annf_get_kernel_times(annf_handle h, annf_kernel_time* out, int32_t capacity, int32_t* count, int32_t reset);

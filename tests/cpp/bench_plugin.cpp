@@ -1,7 +1,8 @@
 // Per-step cost of the bias force THROUGH THE C++ PLUGIN LAYER (ANN_ForceImpl::calcForcesAndEnergy ->
 // CudaCalcANN_ForceKernel::execute -> annf_eval_openmm), i.e. what OpenMM pays per MD step.  BASELINE config 2:
 // alanine dipeptide, 22 atoms, 7 backbone heavy atoms selected, 21-40-4 Tanh/Circular, mixed precision.
-// Prints one JSON object.  usage: bench_plugin [steps]
+// Prints one JSON object.  usage: bench_plugin [steps] [c2|c1]     (c1 = 21-40-2 Tanh/Tanh, the shape the legacy CUDA
+// plugin supports: compare with tools/legacy_restatement)
 #include "OpenMM.h"
 #include "OpenMM_ANN.h"
 #include "CudaANN_KernelFactory.h"
@@ -21,14 +22,15 @@ static double lcg(unsigned long long& s) { s = s * 6364136223846793005ULL + 1442
 
 int main(int argc, char** argv) {
     const int steps = argc > 1 ? atoi(argv[1]) : 20000;
+    const bool c1 = argc > 2 && string(argv[2]) == "c1";
     registerANN_CudaKernelFactories();
     System system;
     const int num_atoms = 22;
     for (int i = 0; i < num_atoms; i++) system.addParticle(12.0);
     ANN_Force* f = new ANN_Force();
-    const vector<int> nodes = {21, 40, 4};
+    const vector<int> nodes = {21, 40, c1 ? 2 : 4};
     f->set_num_of_nodes(nodes);
-    f->set_layer_types({"Tanh", "Circular"});
+    f->set_layer_types({"Tanh", c1 ? "Tanh" : "Circular"});
     unsigned long long seed = 1234;
     vector<vector<double> > coeff(2), bias(2);
     for (int l = 0; l < 2; l++) {
@@ -38,7 +40,7 @@ int main(int argc, char** argv) {
     }
     f->set_coeffients_of_connections(coeff);
     f->set_values_of_biased_nodes(bias);
-    f->set_potential_center({0.7, -1.1});
+    f->set_potential_center(c1 ? vector<double>({0.3, 0.3}) : vector<double>({0.7, -1.1}));
     f->set_force_constant(500);
     f->set_scaling_factor(0.5);
     f->set_index_of_backbone_atoms({2, 5, 7, 9, 15, 17, 19});     // ACE-ALA-NME backbone heavy atoms
@@ -67,8 +69,24 @@ int main(int argc, char** argv) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     const double wall_us = chrono::duration<double, micro>(t1 - t0).count() / steps;
-    printf("{\"steps\": %d, \"gpu_us_per_step\": %.4f, \"wall_us_per_step\": %.4f, \"energy\": %.12g, "
-           "\"path\": \"ANN_ForceImpl::calcForcesAndEnergy -> CudaCalcANN_ForceKernel::execute -> annf_eval_openmm\"}\n",
-           steps, 1e3 * ms / steps, wall_us, e_check);
+    // the same calls replayed from a CUDA graph of 100 steps (what an integrator that graphs its step would see)
+    cudaGraph_t graph; cudaGraphExec_t exec;
+    cudaStreamBeginCapture(cu.getCurrentStream(), cudaStreamCaptureModeGlobal);
+    for (int i = 0; i < 100; i++) force_impl->calcForcesAndEnergy(impl, true, true, 0xFFFFFFFF);
+    cudaStreamEndCapture(cu.getCurrentStream(), &graph);
+    float ms_graph = -1.f;
+    if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphLaunch(exec, cu.getCurrentStream());
+        cudaStreamSynchronize(cu.getCurrentStream());
+        cudaEventRecord(e0, cu.getCurrentStream());
+        for (int i = 0; i < steps / 100; i++) cudaGraphLaunch(exec, cu.getCurrentStream());
+        cudaEventRecord(e1, cu.getCurrentStream());
+        cudaStreamSynchronize(cu.getCurrentStream());
+        cudaEventElapsedTime(&ms_graph, e0, e1);
+    }
+    printf("{\"network\": \"%s\", \"steps\": %d, \"gpu_us_per_step\": %.4f, \"wall_us_per_step\": %.4f, \"graph_us_per_step\": %.4f, "
+           "\"energy\": %.12g, \"path\": \"ANN_ForceImpl::calcForcesAndEnergy -> CudaCalcANN_ForceKernel::execute -> annf_eval_openmm\"}\n",
+           c1 ? "21-40-2 Tanh/Tanh" : "21-40-4 Tanh/Circular", steps, 1e3 * ms / steps, wall_us,
+           ms_graph < 0 ? -1.0 : 1e3 * ms_graph / (steps / 100 * 100), e_check);
     return 0;
 }
