@@ -36,7 +36,7 @@ class Desc(C.Structure):
 class Info(C.Structure):
     _fields_ = [("precision_single", C.c_int32), ("precision_batched", C.c_int32), ("batched_path", C.c_int32),
                 ("cluster_size", C.c_int32), ("macs_per_eval", C.c_int64), ("kernel_launches", C.c_int64),
-                ("sm_count", C.c_int32), ("reserved", C.c_int32)]
+                ("sm_count", C.c_int32), ("single_path", C.c_int32)]
 
 
 class KernelTime(C.Structure):
@@ -57,6 +57,7 @@ SYMBOLS = {
     "annf_eval_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annf_eval_batched_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annf_debug_single_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "annf_debug_stream_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "annf_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "annf_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTime), C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
 }

@@ -22,11 +22,25 @@ cudaError_t prepare_single(const NetView& net, int cluster_size);
 cudaError_t read_single_phase_clocks(long long* out16);
 cudaError_t launch_single(const NetView& net, int cluster_size, const void* posq, const void* posq_corr,
                           unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream);
+bool fast_single_plan(const NetView& net, int cluster_size, const std::vector<std::vector<double>>& w, const std::vector<double>& b64,
+                      FastPlan* plan, std::vector<double>* blobs);
+cudaError_t prepare_single_fast();
+cudaError_t launch_single_fast(const NetView& net, const FastPlan& plan, const double* blobs, const void* posq, const void* posq_corr,
+                               unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream);
 // annf_batched.cu
 size_t batched_smem_bytes(const NetView& net, int extra_nodes, int tr, bool fp64);
 cudaError_t launch_batched(const NetView& net, const int* x_off, int extra_nodes, int tr, bool fp64, int R,
                            const float* coords, int atoms_per_replica, const float* centers, float* forces,
                            double* energies, cudaStream_t stream);
+// annf_stream.cu
+bool build_stream(const NetView& net, const std::vector<std::vector<double>>& w, const std::vector<double>& b64,
+                  const std::vector<int>& sel_atoms, bool fp64, StreamPlan* plan, std::vector<double>* stream64,
+                  std::vector<float>* stream32, std::vector<unsigned char>* statics);
+cudaError_t read_stream_phase_clocks(long long* out32);
+int stream_pick_tile(const NetView& net, const StreamPlan& plan, bool fp64, int R, int sm_count);
+cudaError_t launch_stream(const NetView& net, const StreamPlan& plan, const void* statics_dev, int static_bytes, const void* stream_dev,
+                          bool fp64, int tr, int R, const float* coords, int atoms_per_replica,
+                          const float* centers, float* forces, double* energies, cudaStream_t stream);
 // annf_tensor.cu
 struct TensorPlan;
 TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, std::string* why_not);
@@ -97,6 +111,14 @@ struct annf_context {
     int prec_single = ANNF_PREC_FP64, prec_batched = ANNF_PREC_FP64;
     int batched_path = 0;
     int cluster_size = 1;
+    bool fast_single = false;        // low-latency single-replica kernel applies (Cartesian input, Tanh / Linear hidden layers)
+    FastPlan fast_plan{};
+    double* fast_blobs = nullptr;    // per-CTA parameter blobs of the low-latency single-replica kernel
+    bool streamed = false;           // batched path 2: fused kernel with TMA-streamed weights
+    StreamPlan stream_plan{};
+    void* stream_dev = nullptr;
+    unsigned char* stream_statics = nullptr;   // plan | biases | selection: bulk-copied into shared memory by every CTA
+    int stream_static_bytes = 0;          // [n_0][n_1] first connection, transposed, with the centring / scaling Jacobian folded in
     int tile_fp64 = 1, tile_fp32 = 1;
     int x_off[kMaxLayers];
     int extra_nodes = 0;
@@ -134,7 +156,8 @@ void release(annf_context* h) {
     h->prof.drain();
     if (h->tensor) tensor_plan_destroy(h->tensor);
     cudaFree(h->W64); cudaFree(h->Wt64); cudaFree(h->b64); cudaFree(h->center); cudaFree(h->k_dev); cudaFree(h->staged);
-    cudaFree(h->W32); cudaFree(h->Wt32); cudaFree(h->b32);
+    cudaFree(h->W32); cudaFree(h->Wt32); cudaFree(h->b32); cudaFree(h->fast_blobs);
+    cudaFree(h->stream_dev); cudaFree(h->stream_statics);
     cudaFree(h->sel_atoms); cudaFree(h->sel_slots); cudaFree(h->inverse); cudaFree(h->pairs_local); cudaFree(h->dihedrals_local);
     cudaFree(h->h_coords); cudaFree(h->h_centers); cudaFree(h->h_forces); cudaFree(h->h_energies);
     if (h->staged_host) cudaFreeHost(h->staged_host);
@@ -338,6 +361,14 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
                     single_smem_bytes(net, cl));
     }
     ANNF_CUDA_H(prepare_single(net, cl));
+    {
+        std::vector<double> blobs;
+        h->fast_single = fast_single_plan(net, cl, coeff_rows, b64, &h->fast_plan, &blobs);
+        if (h->fast_single) {
+            ANNF_CUDA_H(upload(&h->fast_blobs, blobs));
+            ANNF_CUDA_H(prepare_single_fast());
+        }
+    }
 
     // batched: extra shared-memory slots for non-elementwise hidden layers
     h->extra_nodes = 0;
@@ -376,7 +407,27 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     }
     h->prec_batched = prec;
     h->batched_path = prec == ANNF_PREC_TF32X3 ? 1 : 0;
-    if ((prec == ANNF_PREC_FP64 && h->tile_fp64 == 0) || (prec == ANNF_PREC_FP32 && h->tile_fp32 == 0)) {
+    if (prec != ANNF_PREC_TF32X3) {
+        std::vector<double> s64;
+        std::vector<float> s32;
+        std::vector<unsigned char> statics;
+        const bool fp64 = prec == ANNF_PREC_FP64;
+        if (build_stream(net, coeff_rows, b64, sel, fp64, &h->stream_plan, &s64, &s32, &statics) &&
+            stream_pick_tile(net, h->stream_plan, fp64, 1, h->sm_count) > 0) {
+            if (fp64) {
+                double* a = nullptr;
+                ANNF_CUDA_H(upload(&a, s64)); h->stream_dev = a;
+            } else {
+                float* a = nullptr;
+                ANNF_CUDA_H(upload(&a, s32)); h->stream_dev = a;
+            }
+            ANNF_CUDA_H(upload(&h->stream_statics, statics));
+            h->stream_static_bytes = (int) statics.size();
+            h->streamed = true;
+            h->batched_path = 2;
+        }
+    }
+    if (!h->streamed && ((prec == ANNF_PREC_FP64 && h->tile_fp64 == 0) || (prec == ANNF_PREC_FP32 && h->tile_fp32 == 0))) {
         release(h);
         return fail(ANNF_ERR_UNSUPPORTED, "network too large for the fused batched kernel's shared memory in this precision");
     }
@@ -409,7 +460,7 @@ annf_status annf_get_info(annf_handle h, annf_info* info) {
     info->macs_per_eval = h->macs;
     info->kernel_launches = h->launches;
     info->sm_count = h->sm_count;
-    info->reserved = 0;
+    info->single_path = h->fast_single ? 1 : 0;
     return ANNF_OK;
 }
 
@@ -453,9 +504,14 @@ annf_status annf_eval_openmm(annf_handle h, const void* posq, const void* posq_c
         return fail(ANNF_ERR_INVALID, "annf_eval_openmm: padded_num_atoms %d < %d atoms", padded_num_atoms, h->num_system_atoms);
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
-    h->prof.begin("annf_single_kernel", s);
-    cudaError_t err = launch_single(h->net, h->cluster_size, posq, posq_correction, force_buffer, padded_num_atoms,
-                                    energy_buffer, flags, s);
+    cudaError_t err;
+    if (h->fast_single) {
+        h->prof.begin("annf_single_fast_kernel", s);
+        err = launch_single_fast(h->net, h->fast_plan, h->fast_blobs, posq, posq_correction, force_buffer, padded_num_atoms, energy_buffer, flags, s);
+    } else {
+        h->prof.begin("annf_single_kernel", s);
+        err = launch_single(h->net, h->cluster_size, posq, posq_correction, force_buffer, padded_num_atoms, energy_buffer, flags, s);
+    }
     h->prof.end(s);
     if (err != cudaSuccess) return fail(ANNF_ERR_CUDA, "single-replica launch failed: %s", cudaGetErrorString(err));
     h->launches++;
@@ -477,6 +533,14 @@ annf_status annf_eval_batched(annf_handle h, int32_t R, const float* coords, int
     if (h->batched_path == 1) {
         err = tensor_plan_run(h->tensor, &h->prof, h->net, R, coords, atoms_per_replica, centers, forces, energies, s, &h->launches,
                               h->tensor_slot);
+    } else if (h->streamed) {
+        const bool fp64 = h->prec_batched == ANNF_PREC_FP64;
+        h->prof.begin(fp64 ? "annf_stream_kernel<f64>" : "annf_stream_kernel<f32>", s);
+        err = launch_stream(h->net, h->stream_plan, h->stream_statics, h->stream_static_bytes, h->stream_dev, fp64,
+                            stream_pick_tile(h->net, h->stream_plan, fp64, R, h->sm_count), R, coords, atoms_per_replica, centers,
+                            forces, energies, s);
+        h->prof.end(s);
+        h->launches++;
     } else {
         const bool fp64 = h->prec_batched == ANNF_PREC_FP64;
         h->prof.begin(fp64 ? "annf_batched_kernel<f64>" : "annf_batched_kernel<f32>", s);
@@ -579,6 +643,14 @@ annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16) {
     DeviceGuard guard(h->device);
     ANNF_CUDA(cudaDeviceSynchronize());
     ANNF_CUDA(read_single_phase_clocks(reinterpret_cast<long long*>(clocks16)));
+    return ANNF_OK;
+}
+
+annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks32) {
+    if (!h || !clocks32) return fail(ANNF_ERR_INVALID, "annf_debug_stream_phases: NULL argument");
+    DeviceGuard guard(h->device);
+    ANNF_CUDA(cudaDeviceSynchronize());
+    ANNF_CUDA(read_stream_phase_clocks(reinterpret_cast<long long*>(clocks32)));
     return ANNF_OK;
 }
 

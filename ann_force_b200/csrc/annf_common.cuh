@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "annforce_b200.h"
+#include "annf_math.cuh"
 
 namespace annf {
 
@@ -40,6 +41,36 @@ struct NetView {
     const int* dihedrals;           // [4*n_dihedrals] indices INTO the feature-atom list
 };
 
+// Low-latency single-replica kernel (annf_single.cu, annf_single_fast_kernel): what the launcher needs to know; the work
+// split itself travels inside the per-CTA parameter blobs.
+struct FastPlan {
+    int cl;                         // CTAs in the cluster (1 = plain launch)
+    int blob_doubles;               // size of one CTA's parameter blob, in doubles
+    int smem_doubles;               // dynamic shared memory of one CTA, in doubles
+};
+
+constexpr int kStreamMaxPass = 2 * (kMaxLayers - 1);
+
+// Host-built description of the weight stream and of the work split of every pass (= one contraction) of the streamed
+// batched kernel (annf_stream.cu).  pass p < L-1 is forward connection l = p; pass p >= L-1 is backward connection
+// l = 2(L-1)-1-p.  A copy lives in device memory and is bulk-copied into shared memory at kernel start, so that the kernel's
+// constant-bank argument block stays small (every first touch of a constant line costs a serialised miss).
+struct StreamPlan {
+    int L, total, npass, scratch_unit;   // scratch_unit: K-split scratch in elements per replica of the tile
+    int nodes[kMaxLayers];
+    int types[kMaxLayers];
+    int node_off[kMaxLayers + 1];
+    int n_lane[kStreamMaxPass];      // outputs of the pass (lane dimension)
+    int n_loop[kStreamMaxPass];      // contraction length (rows of the streamed matrix)
+    int ld[kStreamMaxPass];          // row stride in elements = groups * nc * 32 (zero padded: lanes never leave the row)
+    int rows_per[kStreamMaxPass];    // rows per chunk
+    int nchunks[kStreamMaxPass];
+    int nc[kStreamMaxPass], groups[kStreamMaxPass], ks[kStreamMaxPass];
+    int pad[3];
+    long long base[kStreamMaxPass];  // element offset of the pass in the stream
+};
+static_assert(sizeof(StreamPlan) % 16 == 0, "StreamPlan is bulk-copied: its size must be a multiple of 16 bytes");
+
 template <typename T> struct WeightsOf;
 template <> struct WeightsOf<double> {
     __device__ static const double* W(const NetView& n) { return n.W64; }
@@ -63,7 +94,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__device__ __forceinline__ double act_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ double act_tanh(double x) { return annf_tanh(x); }   // annf_math.cuh: <= 4 ulp, ~20-deep chain
 __device__ __forceinline__ float act_tanh(float x) { return tanhf(x); }
 
 // ---------------------------------------------------------------------------------------------

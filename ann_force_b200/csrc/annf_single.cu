@@ -19,7 +19,12 @@
 // weights stream from L2 (each is used once per direction).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
 #include "annf_common.cuh"
+#include "annf_math.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -44,19 +49,20 @@ struct SingleArgs {
 };
 
 // Position of one atom slot in nm, fp64, honouring single / mixed (+correction) / double layouts.
-__device__ __forceinline__ double3 load_pos(const SingleArgs& a, int slot) {
-    if (a.flags & ANNF_FLAG_POSQ_DOUBLE) {
-        const double4 p = reinterpret_cast<const double4*>(a.posq)[slot];
+__device__ __forceinline__ double3 load_pos(const void* posq, const void* posq_corr, unsigned flags, int slot) {
+    if (flags & ANNF_FLAG_POSQ_DOUBLE) {
+        const double4 p = reinterpret_cast<const double4*>(posq)[slot];
         return make_double3(p.x, p.y, p.z);
     }
-    const float4 p = __ldg(reinterpret_cast<const float4*>(a.posq) + slot);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(posq) + slot);
     double3 r = make_double3((double) p.x, (double) p.y, (double) p.z);
-    if (a.posq_corr != nullptr) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(a.posq_corr) + slot);
+    if (posq_corr != nullptr) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(posq_corr) + slot);
         r.x += (double) c.x; r.y += (double) c.y; r.z += (double) c.z;
     }
     return r;
 }
+__device__ __forceinline__ double3 load_pos(const SingleArgs& a, int slot) { return load_pos(a.posq, a.posq_corr, a.flags, slot); }
 
 // Write v into the same shared-memory location of every CTA of the cluster.
 __device__ __forceinline__ void publish(cg::cluster_group& cluster, int cl, double* local_ptr, double v, int lane) {
@@ -459,6 +465,424 @@ cudaError_t prepare_single(const NetView& net, int cluster_size) {
     if (cluster_size > 8)
         err = cudaFuncSetAttribute(annf_single_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     return err;
+}
+
+// =====================================================================================================================
+// Low-latency variant for the common case: Cartesian input, Tanh / Linear hidden layers, any output layer.
+//
+// One evaluation of a small network is a chain of dependent steps (C2: 4 kFLOP), so the kernel is organised around the
+// number of serialised round trips, not around throughput:
+//   * ONE global-memory round trip for parameters: every CTA pulls exactly the weight rows it will use — its row slice of
+//     every W_l for the forward pass, its row slice of every W_l^T for the backward pass, biases, centre, k — into shared
+//     memory with cp.async before it touches the positions; the copies land while the positions are gathered;
+//   * ONE barrier per layer: the lane that finishes a row's dot product applies bias + activation (forward) or the
+//     activation derivative (backward) itself and publishes the result (DSMEM stores when the network spans a cluster);
+//     a Tanh / Linear output layer gets its energy term and output gradient in the same epilogue;
+//   * the first connection's backward matrix is stored pre-centred and pre-scaled,
+//        W0c^T[t][k] = -(1/s) (W_0[k][t] - (1/A) sum_i W_0[k][3i+c(t)]),
+//     i.e. the Jacobian of "divide by s, subtract the centroid" (ANN_ReferenceKernels.cpp:137-145, :397-410) folded into
+//     the weights, so the last mat-vec yields forces and its epilogue is the fixed-point atomicAdd: no mean, no extra pass;
+//   * a dot product is shared by 2^lg lanes chosen on the host per layer (few lanes = few shuffle rounds).
+// =====================================================================================================================
+// Per-CTA parameter block ("blob"), built on the host at create time and fetched with ONE bulk copy (TMA engine) per
+// CTA: a 512-byte integer header (network shape + work split of this CTA) followed by exactly the weight rows the CTA
+// uses, already in their shared-memory layout.  Keeping the kernel's argument struct to a few dozen bytes matters as much
+// as the single copy: every first touch of a 64-byte line of the constant-bank argument block is a serialised miss
+// (measured: ~2,000 cycles of the old prologue went into walking per-layer arrays passed by value).
+enum {
+    kHdrL = 0, kHdrTotal, kHdrNL, kHdrNodes = 8, kHdrTypes = 16, kHdrNodeOff = 24,
+    kHdrFRows = 40, kHdrFLg = 48, kHdrFOff = 56, kHdrFbOff = 64, kHdrFJ0 = 72,
+    kHdrBRows = 80, kHdrBLg = 88, kHdrBOff = 96, kHdrBM0 = 104, kHdrInts = 128
+};
+
+struct FastArgs {
+    const double* blob;         // cluster_size blobs, blob_doubles apart
+    int blob_doubles;
+    int A, num_center, total, nL;
+    const int* sel_slots;
+    const double* center;
+    const double* k_dev;
+    double inv_scale, inv_A;
+    const void* posq;
+    const void* posq_corr;
+    unsigned long long* force;
+    int padded;
+    unsigned flags;
+    void* energy;
+};
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t) __cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
+// out[r] = sum_c M[r][c] * v[c] for r < nrows (M rows contiguous in shared memory); 2^lg lanes of one warp share a row and
+// the lane with g == 0 receives the sum in epi(r, sum).  Called by every thread of the CTA.
+// The terms of a lane are taken 16 at a time with every load issued before the first FMA: the loop is latency-bound, and
+// a strided loop with run-time bounds costs ~90 cycles per 4 terms.
+template <typename Epi>
+__device__ __forceinline__ void fast_matvec(const double* M, int ncols, int nrows, const double* v, int lg, Epi epi) {
+    const int tid = threadIdx.x;
+    const int G = 1 << lg, g = tid & (G - 1), slot = tid >> lg, rows_per_pass = kSingleThreads >> lg;
+    for (int r0 = 0; r0 < nrows; r0 += rows_per_pass) {        // trip count is uniform over the CTA
+        const int r = r0 + slot;
+        const bool valid = r < nrows;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        if (valid) {
+            const double* row = M + (size_t) r * ncols;
+            for (int c0 = g; c0 < ncols; c0 += 16 * G) {
+                double w[16], x[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const int c = c0 + u * G;
+                    const bool in = c < ncols;
+                    w[u] = in ? row[c] : 0.0;
+                    x[u] = in ? v[c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    acc0 = fma(w[u], x[u], acc0);
+                    acc1 = fma(w[u + 1], x[u + 1], acc1);
+                    acc2 = fma(w[u + 2], x[u + 2], acc2);
+                    acc3 = fma(w[u + 3], x[u + 3], acc3);
+                }
+            }
+        }
+        double sum = (acc0 + acc1) + (acc2 + acc3);
+        for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (valid && g == 0) epi(r, sum);
+    }
+}
+
+template <bool kCluster>
+__global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(const FastArgs args) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cl = 1, rank = 0;
+    if (kCluster) {
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cl));
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        // every CTA must be running before anyone stores into a peer's shared memory: arrive now, wait after the prologue
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    }
+    // Programmatic dependent launch: the next kernel of the stream may start its own prologue now; this one fetches its
+    // (static) parameters first and only then waits for the kernels before it — the integrator that wrote the positions.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    ANNF_PHASE(0);
+
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long blob_bar;
+    const int total = args.total, nL = args.nL, A = args.A;
+    double* blob = smem;                                  // header + this CTA's weight rows
+    const int* hdr = reinterpret_cast<const int*>(blob);
+    double* a = blob + args.blob_doubles;                 // activations, all layers
+    double* d = a + total;                                // dE/dz, all layers
+    double* zL = d + total;                               // output pre-activations (non-elementwise heads only)
+    double* eterm = zL + nL;                              // energy terms of the outputs
+    double* cen = eterm + nL;                             // umbrella centre
+    double* kval = cen + args.num_center;                 // force constant
+    double* red = kval + 1;                               // [3 * warps] centroid partial sums, [3] centroid
+    int* slots_s = reinterpret_cast<int*>(red + 3 * kSingleWarps + 4);   // position-buffer slot of every selected atom
+
+    // ---- parameters: one bulk copy + two tiny cp.async, consumed after the positions are in -----------------------
+    const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&blob_bar);
+    if (tid == kSingleThreads - 32) {                     // first lane of the last warp: warp 0 goes straight to the positions
+        const uint32_t bytes = (uint32_t) args.blob_doubles * 8u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t) __cvta_generic_to_shared(blob)),
+                       "l"(__cvta_generic_to_global(args.blob + (size_t) rank * args.blob_doubles)), "r"(bytes), "r"(bar) : "memory");
+    }
+    if (warp == 1) {
+        for (int i = lane; i < args.num_center; i += 32) cp_async8(cen + i, args.center + i);
+        if (lane == 31) cp_async8(kval, args.k_dev);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");    // everything below may read what earlier kernels wrote
+    ANNF_PHASE(11);
+
+    // ---- feature stage: ANN_ReferenceKernels.cpp:128-151 (every CTA builds the full centred input) ----------------
+    if (A <= 32) {
+        // the whole selection sits in warp 0: butterfly sums leave the centroid in every lane, no block-level hop
+        if (warp == 0) {
+            double x = 0.0, y = 0.0, w = 0.0;
+            if (lane < A) {
+                const int slot = args.sel_slots[lane];
+                slots_s[lane] = slot;
+                const double3 p = load_pos(args.posq, args.posq_corr, args.flags, slot);
+                x = p.x * args.inv_scale; y = p.y * args.inv_scale; w = p.z * args.inv_scale;      // :139
+            }
+            double sx = x, sy = y, sz = w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            }
+            if (lane < A) {                                                                         // :137-145
+                a[3 * lane] = x - sx * args.inv_A;
+                a[3 * lane + 1] = y - sy * args.inv_A;
+                a[3 * lane + 2] = w - sz * args.inv_A;
+            }
+        }
+    } else {
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int i = tid; i < A; i += kSingleThreads) {
+            const int slot = args.sel_slots[i];
+            slots_s[i] = slot;
+            const double3 p = load_pos(args.posq, args.posq_corr, args.flags, slot);
+            const double x = p.x * args.inv_scale, y = p.y * args.inv_scale, w = p.z * args.inv_scale;
+            a[3 * i] = x; a[3 * i + 1] = y; a[3 * i + 2] = w;
+            sx += x; sy += y; sz += w;
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        if (lane == 0) { red[3 * warp] = sx; red[3 * warp + 1] = sy; red[3 * warp + 2] = sz; }
+        __syncthreads();
+        if (tid < 3) {
+            double t = 0.0;
+            for (int w = 0; w < kSingleWarps; w++) t += red[3 * w + tid];
+            red[3 * kSingleWarps + tid] = t * args.inv_A;
+        }
+        __syncthreads();
+        for (int i = tid; i < 3 * A; i += kSingleThreads) a[i] -= red[3 * kSingleWarps + i % 3];
+    }
+    ANNF_PHASE(1);
+    if (warp == 1) asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                      // also orders the mbarrier init before everyone's wait
+    {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0, 0x989680;\n\t"
+            "@P1 bra DONE_%=;\n\t"
+            "bra WAIT_%=;\n\t"
+            "DONE_%=:\n\t"
+            "}" ::"r"(bar) : "memory");
+    }
+    if (kCluster) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    ANNF_PHASE(2);
+
+    auto publish = [&](double* local, double v) {
+        if (!kCluster) {
+            *local = v;
+        } else {
+            const uint32_t addr = (uint32_t) __cvta_generic_to_shared(local);
+            for (int r = 0; r < cl; r++) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(r));
+                asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+            }
+        }
+    };
+    auto sync_all = [&]() {
+        if (!kCluster) {
+            __syncthreads();
+        } else {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+    };
+
+    // ---- forward: calculate_output_of_each_layer, ANN_ReferenceKernels.cpp:179-260 --------------------------------
+    const int L = hdr[kHdrL];
+    const double kk = *kval;
+    for (int l = 0; l + 1 < L; l++) {
+        const int n_in = hdr[kHdrNodes + l];
+        const int j0 = hdr[kHdrFJ0 + l], nf = hdr[kHdrFRows + l];
+        const double* bias = blob + hdr[kHdrFbOff + l];
+        const int type = hdr[kHdrTypes + l];
+        const bool last = l + 2 == L;
+        double* out = a + hdr[kHdrNodeOff + l + 1];
+        double* dzL = d + hdr[kHdrNodeOff + L - 1];
+        fast_matvec(blob + hdr[kHdrFOff + l], n_in, nf, a + hdr[kHdrNodeOff + l], hdr[kHdrFLg + l], [&](int r, double sum) {
+            const int j = j0 + r;
+            const double zz = sum + bias[r];                                                        // :193-198
+            if (!last) {
+                publish(out + j, type == ANNF_TANH ? annf_tanh(zz) : zz);                           // :200-209
+            } else if (type == ANNF_TANH || type == ANNF_LINEAR) {
+                // output head of an element-wise layer, in the lane that owns the output (same expressions as output_head)
+                const double av = (type == ANNF_TANH) ? annf_tanh(zz) : zz;
+                const double dd = (av - cen[j]) * kk;                                               // :266-269
+                publish(eterm + j, 0.5 * kk * (av - cen[j]) * (av - cen[j]));                       // .h:93-96
+                publish(dzL + j, (type == ANNF_TANH) ? dd * (1 - av * av) : dd);                    // :343-354
+            } else {
+                publish(zL + j, zz);
+            }
+        });
+        sync_all();
+        if (l < 2) ANNF_PHASE(7 + 2 * l);
+        if (last && !(type == ANNF_TANH || type == ANNF_LINEAR)) {
+            // Circular / Softmax output: needs the whole output vector (identical in every CTA)
+            for (int t = tid; t < nL; t += kSingleThreads)
+                eterm[t] = output_head_parallel(type, nL, zL, 1, cen, kk, dzL, 1, t);
+            __syncthreads();
+        }
+    }
+    ANNF_PHASE(3);
+    if (rank == 0 && tid == kSingleThreads - 1 && args.energy != nullptr && !(args.flags & ANNF_FLAG_SKIP_ENERGY)) {
+        double e = 0.0;
+        for (int t = 0; t < nL; t++) e += eterm[t];
+        if (args.flags & ANNF_FLAG_ENERGY_DOUBLE) atomicAdd(reinterpret_cast<double*>(args.energy), e);
+        else atomicAdd(reinterpret_cast<float*>(args.energy), (float) e);
+    }
+    ANNF_PHASE(4);
+
+    // ---- backward: back_prop, ANN_ReferenceKernels.cpp:299-373, ending in the forces (:397-410) --------------------
+    if (!(args.flags & ANNF_FLAG_SKIP_FORCES)) {
+        for (int l = L - 2; l >= 0; l--) {
+            const int n_out = hdr[kHdrNodes + l + 1];
+            const int m0 = hdr[kHdrBM0 + l], nb = hdr[kHdrBRows + l];
+            const int type = l >= 1 ? hdr[kHdrTypes + l - 1] : ANNF_LINEAR;
+            const double* al = a + hdr[kHdrNodeOff + l];
+            double* dl = d + hdr[kHdrNodeOff + l];
+            fast_matvec(blob + hdr[kHdrBOff + l], n_out, nb, d + hdr[kHdrNodeOff + l + 1], hdr[kHdrBLg + l], [&](int r, double sum) {
+                const int m = m0 + r;
+                if (l >= 1) {
+                    const double av = al[m];
+                    publish(dl + m, type == ANNF_TANH ? sum * (1 - av * av) : sum);                 // :343-354
+                } else {
+                    const int i = m / 3, c = m - 3 * i;
+                    atomicAdd(&args.force[slots_s[i] + c * args.padded],
+                              (unsigned long long) ((long long) (sum * (double) 0x100000000LL)));
+                }
+            });
+            if (l >= 1) sync_all();
+        }
+    }
+    ANNF_PHASE(5);
+    ANNF_PHASE(6);
+    // a CTA must not exit while peers may still store into its shared memory: the last publish is followed by sync_all above
+}
+
+// Latency model of one mat-vec (cycles), calibrated on B200 phase clocks: blocks of <= 16 terms per lane whose loads are
+// all in flight together, a shuffle round per halving, per pass.
+static int pick_lanes_log2(int nrows, int ncols) {
+    int forced = -1;
+    if (const char* env = getenv("ANNF_SINGLE_LG")) forced = atoi(env);
+    int best = 0;
+    double best_cost = 1e30;
+    for (int lg = 0; lg <= 5; lg++) {
+        const int G = 1 << lg;
+        if (lg > 0 && G > ncols) break;
+        const int terms = (ncols + G - 1) / G;
+        const int blocks = (terms + 15) / 16;
+        const int passes = (nrows * G + kSingleThreads - 1) / kSingleThreads;
+        const double cost = (passes > 0 ? passes : 1) * (blocks * (40.0 + 6.5 * (terms < 16 ? terms : 16)) + 65.0 * lg);
+        if (cost < best_cost) { best_cost = cost; best = lg; }
+    }
+    if (forced >= 0 && forced <= 5 && (1 << forced) <= (ncols > 1 ? ncols : 1)) best = forced;
+    return best;
+}
+
+// Eligibility, work split and the per-CTA parameter blobs (host vector; the caller uploads it).
+// w[l] are the fp64 weights of connection l, row-major [n_out][n_in]; b64 the flat biases (net.b_off).
+bool fast_single_plan(const NetView& net, int cluster_size, const std::vector<std::vector<double>>& w, const std::vector<double>& b64,
+                      FastPlan* plan, std::vector<double>* blobs) {
+    if (net.input_type != ANNF_INPUT_CARTESIAN) return false;
+    const int L = net.L;
+    for (int l = 0; l + 2 < L; l++)
+        if (net.types[l] != ANNF_TANH && net.types[l] != ANNF_LINEAR) return false;
+    if (net.nodes[L - 1] > 256) return false;
+    if (getenv("ANNF_SINGLE_GENERIC")) return false;
+    const int cl = cluster_size, A = net.n_sel;
+    // pre-centred, pre-scaled transpose of the first connection: F_t = -(1/s) (g_t - mean_c), g = W_0^T dz_1
+    const int n0 = net.nodes[0], n1 = net.nodes[1];
+    std::vector<double> wsum(3 * (size_t) n1, 0.0), wt0c((size_t) n0 * n1);
+    for (int k = 0; k < n1; k++)
+        for (int t = 0; t < n0; t++) wsum[(size_t) (t % 3) * n1 + k] += w[0][(size_t) k * n0 + t];
+    for (int t = 0; t < n0; t++)
+        for (int k = 0; k < n1; k++)
+            wt0c[(size_t) t * n1 + k] = -(w[0][(size_t) k * n0 + t] - wsum[(size_t) (t % 3) * n1 + k] / A) / net.scale;
+    // layout of one blob (identical offsets in every CTA)
+    int f_per[kMaxLayers], b_per[kMaxLayers], f_off[kMaxLayers], fb_off[kMaxLayers], b_off[kMaxLayers];
+    size_t off = kHdrInts / 2;
+    for (int l = 0; l + 1 < L; l++) {
+        const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+        f_per[l] = (n_out + cl - 1) / cl;
+        b_per[l] = (n_in + cl - 1) / cl;
+        f_off[l] = (int) off;  off += (size_t) f_per[l] * n_in;
+        fb_off[l] = (int) off; off += f_per[l];
+        b_off[l] = (int) off;  off += (size_t) b_per[l] * n_out;
+    }
+    off += off & 1;                                           // bulk copies move multiples of 16 bytes
+    const size_t blob_doubles = off;
+    blobs->assign(blob_doubles * cl, 0.0);
+    for (int rank = 0; rank < cl; rank++) {
+        double* blob = blobs->data() + blob_doubles * rank;
+        int* hdr = reinterpret_cast<int*>(blob);
+        hdr[kHdrL] = L; hdr[kHdrTotal] = net.node_off[L]; hdr[kHdrNL] = net.nodes[L - 1];
+        for (int l = 0; l < L; l++) { hdr[kHdrNodes + l] = net.nodes[l]; hdr[kHdrNodeOff + l] = net.node_off[l]; }
+        hdr[kHdrNodeOff + L] = net.node_off[L];
+        for (int l = 0; l + 1 < L; l++) {
+            const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+            const int j0 = rank * f_per[l], nf = std::max(0, std::min(f_per[l], n_out - j0));
+            const int m0 = rank * b_per[l], nb = std::max(0, std::min(b_per[l], n_in - m0));
+            hdr[kHdrTypes + l] = net.types[l];
+            hdr[kHdrFRows + l] = nf; hdr[kHdrFLg + l] = pick_lanes_log2(f_per[l], n_in); hdr[kHdrFOff + l] = f_off[l];
+            hdr[kHdrFbOff + l] = fb_off[l]; hdr[kHdrFJ0 + l] = j0;
+            hdr[kHdrBRows + l] = nb; hdr[kHdrBLg + l] = pick_lanes_log2(b_per[l], n_out); hdr[kHdrBOff + l] = b_off[l];
+            hdr[kHdrBM0 + l] = m0;
+            for (int r = 0; r < nf; r++) {
+                for (int c = 0; c < n_in; c++) blob[f_off[l] + (size_t) r * n_in + c] = w[l][(size_t) (j0 + r) * n_in + c];
+                blob[fb_off[l] + r] = b64[net.b_off[l] + j0 + r];
+            }
+            for (int r = 0; r < nb; r++)
+                for (int c = 0; c < n_out; c++)
+                    blob[b_off[l] + (size_t) r * n_out + c] = l == 0 ? wt0c[(size_t) (m0 + r) * n_out + c] : w[l][(size_t) c * n_in + m0 + r];
+        }
+    }
+    plan->cl = cl;
+    plan->blob_doubles = (int) blob_doubles;
+    const int total = net.node_off[L], nL = net.nodes[L - 1];
+    plan->smem_doubles = (int) (blob_doubles + 2 * (size_t) total + 2 * (size_t) nL + net.num_center + 1 + 3 * kSingleWarps + 4 +
+                                ((size_t) A + 1) / 2 + 2);
+    return (size_t) plan->smem_doubles * sizeof(double) <= 200 * 1024;
+}
+
+cudaError_t prepare_single_fast() {
+    cudaError_t err = cudaFuncSetAttribute(annf_single_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(annf_single_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+}
+
+cudaError_t launch_single_fast(const NetView& net, const FastPlan& plan, const double* blobs, const void* posq, const void* posq_corr,
+                               unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream) {
+    FastArgs args;
+    args.blob = blobs;
+    args.blob_doubles = plan.blob_doubles;
+    args.A = net.n_sel;
+    args.num_center = net.num_center;
+    args.total = net.node_off[net.L];
+    args.nL = net.nodes[net.L - 1];
+    args.sel_slots = net.sel_slots;
+    args.center = net.center;
+    args.k_dev = net.k_dev;
+    args.inv_scale = 1.0 / net.scale;
+    args.inv_A = 1.0 / net.n_sel;
+    args.posq = posq;
+    args.posq_corr = posq_corr;
+    args.force = force;
+    args.padded = padded;
+    args.energy = energy;
+    args.flags = flags;
+    const size_t smem = sizeof(double) * (size_t) plan.smem_doubles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.cl);
+    cfg.blockDim = dim3(kSingleThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see griddepcontrol in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = plan.cl;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = plan.cl == 1 ? 1 : 2;
+    if (plan.cl == 1) return cudaLaunchKernelEx(&cfg, annf_single_fast_kernel<false>, args);
+    return cudaLaunchKernelEx(&cfg, annf_single_fast_kernel<true>, args);
 }
 
 }  // namespace annf

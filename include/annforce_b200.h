@@ -87,12 +87,12 @@ typedef struct {
 typedef struct {
     int32_t precision_single;             /* resolved ANNF_PREC_* of annf_eval_openmm */
     int32_t precision_batched;            /* resolved ANNF_PREC_* of annf_eval_batched */
-    int32_t batched_path;                 /* 0 fused per-CTA kernel, 1 layer-wise tensor-core path */
+    int32_t batched_path;                 /* 0 generic fused per-CTA kernel, 1 layer-wise tensor-core path, 2 fused kernel with TMA-streamed weights */
     int32_t cluster_size;                 /* CTAs per cluster of the single-replica kernel */
     int64_t macs_per_eval;                /* M = sum n_l * n_{l+1} */
     int64_t kernel_launches;              /* kernels launched through this handle since creation */
     int32_t sm_count;
-    int32_t reserved;
+    int32_t single_path;                  /* 0 generic cluster kernel, 1 low-latency kernel (Cartesian input, Tanh / Linear hidden layers) */
 } annf_info;
 
 /* One named kernel's accumulated device time while profiling is on (annf_set_profiling). */
@@ -155,6 +155,11 @@ ANNF_API annf_status annf_eval_batched_host(annf_handle h, int32_t num_replicas,
 /* Diagnostic: SM clock (clock64) of thread 0 at the phase boundaries of the most recent annf_eval_openmm launch:
  * [0] start, [1] features, [2] weights staged, [3] forward, [4] energy head, [5] backward, [6] forces issued.  Synchronises. */
 ANNF_API annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16);
+
+/* Diagnostic: the same for CTA 0 of the most recent streamed batched launch (annf_eval_batched, batched_path 2):
+ * [0] start, [1] prologue loads, [2] features, [3 + p] contraction p done (forward then backward), then head and end;
+ * [32 + p] cycles warp 0 waited for weights in contraction p, [48 + p] its epilogue.  64 values.  Synchronises. */
+ANNF_API annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks64);
 
 /* Per-kernel device timing with CUDA events on the launching stream (for the roofline line). */
 ANNF_API annf_status annf_set_profiling(annf_handle h, int32_t enabled);

@@ -120,3 +120,15 @@ def test_force_mirror_validates_like_the_reference_asserts():
     assert h.get_list_of_index_of_atoms_forming_dihedrals() == [[0, 1, 2, 3], [2, 3, 4, 5]]
     h.set_list_of_pair_index_for_distances([[1, 2], [3, 4]])
     assert h.get_list_of_pair_index_for_distances() == [[0, 1], [2, 3]]
+
+
+def test_device_tanh_matches_long_double():
+    """The short-dependency-chain fp64 tanh of the single-replica kernel (csrc/annf_math.cuh), host build, swept against
+    tanhl: at most 4 ulp anywhere, exact at 0 and in saturation, sign-symmetric."""
+    import json
+    import subprocess
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.run(["make", "-C", cpp, os.path.join(cpp, "_build", "tanh_check")], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(cpp, "_build", "tanh_check")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert json.loads(out.stdout)["worst_ulp"] <= 4.0

@@ -443,3 +443,98 @@ def test_tensor_path_capacity_growth_and_reuse():
     e_h, f_h = kernel.execute_batched_host(pos)
     np.testing.assert_array_equal(e_h, e_dev)
     np.testing.assert_array_equal(f_h, f_dev)
+
+
+# ------------------------------------------------------------------------------------------------------
+# kernel variants: the low-latency / streamed kernels are the default where they apply; the generic
+# kernels (every layer type, every input type) stay covered through the documented environment switches
+# ------------------------------------------------------------------------------------------------------
+ELEMENTWISE_GOLDEN = [n for n in CARTESIAN_GOLDEN if n.startswith(("ref_cartesian", "ref_sweep", "syn_"))]
+
+
+def test_default_kernel_selection():
+    force = synthetic.make_config("c2")
+    kernel = CalcANNForce()
+    kernel.initialize(7, force)
+    info = kernel.info()
+    assert info["single_path"] == "low-latency" and info["batched_path"] == "stream"
+    pairs = _pair_force(10, 6, seed=3)
+    kernel = CalcANNForce()
+    kernel.initialize(10, pairs)
+    info = kernel.info()
+    assert info["single_path"] == "generic" and info["batched_path"] == "fused"
+
+
+@pytest.mark.parametrize("name", ELEMENTWISE_GOLDEN)
+def test_generic_kernels_still_match_golden(name, monkeypatch):
+    monkeypatch.setenv("ANNF_SINGLE_GENERIC", "1")
+    monkeypatch.setenv("ANNF_BATCHED_GENERIC", "1")
+    force, pos, centers, energies, forces, _ = golden_io.load(name)
+    e, frc, seen, kernel = run_single(force, pos[0], "double")
+    assert kernel.info()["single_path"] == "generic" and kernel.info()["batched_path"] in ("fused", "tensor")
+    f0 = force
+    if centers is not None:
+        f0, _, _, _, _, _ = golden_io.load(name)
+        f0.set_potential_center(centers[0])
+        e, frc, seen, kernel = run_single(f0, pos[0], "double")
+    e_ref, f_ref = port.evaluate(f0, pos[0])
+    assert abs(e - e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(frc - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+    pos32 = pos.astype(np.float32)
+    cen32 = None if centers is None else centers.astype(np.float32)
+    eb, fb, _ = run_batched(force, pos32, cen32, precision="fp64")
+    e_ref, f_ref = port.evaluate(force, pos32.astype(np.float64), None if cen32 is None else cen32.astype(np.float64))
+    np.testing.assert_allclose(eb, e_ref, rtol=1e-11)
+    assert max_norm_rel(fb, f_ref) <= 1e-6
+
+
+@pytest.mark.parametrize("tile", ["1", "2", "4", "8"])
+@pytest.mark.parametrize("precision,e_tol,f_tol", [("fp64", 1e-11, 1e-6), ("fp32", 2e-5, F_RTOL)])
+def test_streamed_kernel_every_tile_size(tile, precision, e_tol, f_tol, monkeypatch):
+    """The streamed kernel at every replicas-per-CTA setting: ragged last tile, per-replica centres, the bulk
+    (16-byte aligned) and the gather coordinate paths, a selection inside a larger system."""
+    monkeypatch.setenv("ANNF_STREAM_TR", tile)
+    for n_atoms, sel, R in [(60, list(range(1, 61)), 37), (23, [2, 3, 5, 7, 11, 13, 17, 19, 23], 21)]:
+        nodes = [3 * len(sel), 100, 100, 3] if n_atoms == 60 else [27, 33, 5, 4]
+        types = ["Tanh", "Tanh", "Tanh"] if n_atoms == 60 else ["Tanh", "Linear", "Circular"]
+        force = synthetic.make_force(nodes, types, len(sel), seed=41, atom_index=sel)
+        pos = synthetic.make_positions(n_atoms, R, seed=R)
+        cen = synthetic.make_centers(force, R, seed=R + 1)
+        e, f, kernel = run_batched(force, pos, cen, precision=precision)
+        assert kernel.info()["batched_path"] == "stream"
+        e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+        np.testing.assert_allclose(e, e_ref, rtol=e_tol)
+        assert max_norm_rel(f, f_ref) <= f_tol
+
+
+def test_streamed_kernel_unaligned_coordinates_and_wide_layers():
+    """Coordinates that start at an address that is not 16-byte aligned take the gather path; layers wider than
+    512 nodes give every warp two 32-node chunks and no K-split."""
+    force = synthetic.make_force([21, 600, 70, 2], ["Tanh", "Linear", "Tanh"], 7, seed=8)
+    R = 19
+    pos = synthetic.make_positions(7, R + 1, seed=9).astype(np.float32)
+    flat = torch.as_tensor(pos.reshape(-1), device="cuda")
+    coords = flat[21:].view(R, 7, 3)              # 84-byte offset
+    kernel = CalcANNForce(precision="fp64")
+    kernel.initialize(7, force)
+    assert kernel.info()["batched_path"] == "stream"
+    e, f = kernel.execute_batched(coords)
+    torch.cuda.synchronize()
+    e_ref, f_ref = port.evaluate(force, pos[1:].astype(np.float64))
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=1e-11)
+    assert max_norm_rel(f.double().cpu().numpy(), f_ref) <= 1e-6
+
+
+@pytest.mark.parametrize("lg", ["0", "2", "5"])
+def test_low_latency_single_kernel_lane_groupings(lg, monkeypatch):
+    """The single-replica kernel's dot products shared by 1, 4 or 32 lanes; one CTA and a cluster."""
+    monkeypatch.setenv("ANNF_SINGLE_LG", lg)
+    for config in ("c2", "c4"):
+        cfg = synthetic.CONFIGS[config]
+        force = synthetic.make_config(config)
+        pos = synthetic.make_positions(cfg["atoms"], 1, seed=77)[0]
+        e, frc, seen, kernel = run_single(force, pos, "mixed")
+        assert kernel.info()["single_path"] == "low-latency"
+        e_ref, f_ref = port.evaluate(force, seen)
+        assert abs(e - e_ref) <= 1e-11 * abs(e_ref)
+        assert np.abs(frc - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP

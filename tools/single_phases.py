@@ -14,6 +14,8 @@ for cfg in ("c1", "c2", "c4"):
     buf = (C.c_int64 * 16)()
     _capi.check(_capi.lib().annf_debug_single_phases(k._handle, buf))
     full = np.array(buf[:11])
-    print(cfg, "forward detail: matvec0", int(full[7] - full[2]), "act0", int(full[8] - full[7]), "matvec1", int(full[9] - full[8]), "act1", int(full[10] - full[9]))
+    print(cfg, k.info()["single_path"], "forward detail: connection 0 (+activation)", int(full[7] - full[2]), "connection 1", int(full[9] - full[7]))
+    full = np.array(buf[:16])
+    print(cfg, "prologue: copies issued", int(full[11] - full[0]), "features done", int(full[1] - full[11]))
     t = np.array(buf[:7]); d = np.diff(t)
     print(cfg, "cycles:", dict(zip(["features", "stage-wait", "forward", "head", "backward", "forces"], d.tolist())), "total", int(t[6] - t[0]))
