@@ -41,6 +41,13 @@ int stream_pick_tile(const NetView& net, const StreamPlan& plan, bool fp64, int 
 cudaError_t launch_stream(const NetView& net, const StreamPlan& plan, const void* statics_dev, int static_bytes, const void* stream_dev,
                           bool fp64, int tr, int R, const float* coords, int atoms_per_replica,
                           const float* centers, float* forces, double* energies, cudaStream_t stream);
+// annf_dmma.cu
+bool build_dmma_stream(const NetView& net, const std::vector<std::vector<double>>& w, const std::vector<double>& b64,
+                       const std::vector<int>& sel, StreamPlan* plan, std::vector<double>* stream, std::vector<unsigned char>* statics);
+cudaError_t launch_dmma(const NetView& net, const StreamPlan& plan, const void* statics_dev, int static_bytes, const double* stream_dev,
+                        int R, const float* coords, int atoms_per_replica, const float* centers, float* forces, double* energies,
+                        cudaStream_t stream);
+cudaError_t read_dmma_phase_clocks(long long* out64);
 // annf_tensor.cu
 struct TensorPlan;
 TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, std::string* why_not);
@@ -114,6 +121,7 @@ struct annf_context {
     bool fast_single = false;        // low-latency single-replica kernel applies (Cartesian input, Tanh / Linear hidden layers)
     FastPlan fast_plan{};
     double* fast_blobs = nullptr;    // per-CTA parameter blobs of the low-latency single-replica kernel
+    bool dmma = false;               // batched path 3: the streamed kernel on the FP64 tensor path (fp64 only)
     bool streamed = false;           // batched path 2: fused kernel with TMA-streamed weights
     StreamPlan stream_plan{};
     void* stream_dev = nullptr;
@@ -412,7 +420,14 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
         std::vector<float> s32;
         std::vector<unsigned char> statics;
         const bool fp64 = prec == ANNF_PREC_FP64;
-        if (build_stream(net, coeff_rows, b64, sel, fp64, &h->stream_plan, &s64, &s32, &statics) &&
+        if (fp64 && build_dmma_stream(net, coeff_rows, b64, sel, &h->stream_plan, &s64, &statics)) {
+            double* a = nullptr;
+            ANNF_CUDA_H(upload(&a, s64)); h->stream_dev = a;
+            ANNF_CUDA_H(upload(&h->stream_statics, statics));
+            h->stream_static_bytes = (int) statics.size();
+            h->dmma = true;
+            h->batched_path = 3;
+        } else if (build_stream(net, coeff_rows, b64, sel, fp64, &h->stream_plan, &s64, &s32, &statics) &&
             stream_pick_tile(net, h->stream_plan, fp64, 1, h->sm_count) > 0) {
             if (fp64) {
                 double* a = nullptr;
@@ -427,7 +442,7 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
             h->batched_path = 2;
         }
     }
-    if (!h->streamed && ((prec == ANNF_PREC_FP64 && h->tile_fp64 == 0) || (prec == ANNF_PREC_FP32 && h->tile_fp32 == 0))) {
+    if (!h->streamed && !h->dmma && ((prec == ANNF_PREC_FP64 && h->tile_fp64 == 0) || (prec == ANNF_PREC_FP32 && h->tile_fp32 == 0))) {
         release(h);
         return fail(ANNF_ERR_UNSUPPORTED, "network too large for the fused batched kernel's shared memory in this precision");
     }
@@ -533,6 +548,12 @@ annf_status annf_eval_batched(annf_handle h, int32_t R, const float* coords, int
     if (h->batched_path == 1) {
         err = tensor_plan_run(h->tensor, &h->prof, h->net, R, coords, atoms_per_replica, centers, forces, energies, s, &h->launches,
                               h->tensor_slot);
+    } else if (h->dmma) {
+        h->prof.begin("annf_dmma_kernel<f64>", s);
+        err = launch_dmma(h->net, h->stream_plan, h->stream_statics, h->stream_static_bytes, (const double*) h->stream_dev, R, coords,
+                          atoms_per_replica, centers, forces, energies, s);
+        h->prof.end(s);
+        h->launches++;
     } else if (h->streamed) {
         const bool fp64 = h->prec_batched == ANNF_PREC_FP64;
         h->prof.begin(fp64 ? "annf_stream_kernel<f64>" : "annf_stream_kernel<f32>", s);
@@ -650,7 +671,8 @@ annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks32) {
     if (!h || !clocks32) return fail(ANNF_ERR_INVALID, "annf_debug_stream_phases: NULL argument");
     DeviceGuard guard(h->device);
     ANNF_CUDA(cudaDeviceSynchronize());
-    ANNF_CUDA(read_stream_phase_clocks(reinterpret_cast<long long*>(clocks32)));
+    if (h->dmma) ANNF_CUDA(read_dmma_phase_clocks(reinterpret_cast<long long*>(clocks32)));
+    else ANNF_CUDA(read_stream_phase_clocks(reinterpret_cast<long long*>(clocks32)));
     return ANNF_OK;
 }
 

@@ -89,7 +89,7 @@ class CalcANNForce:
         _capi.check(_capi.lib().annf_get_info(self._handle, C.byref(info)))
         return dict(precision_single=_capi.PRECISION_NAMES[info.precision_single],
                     precision_batched=_capi.PRECISION_NAMES[info.precision_batched],
-                    batched_path={0: "fused", 1: "tensor", 2: "stream"}[info.batched_path],
+                    batched_path={0: "fused", 1: "tensor", 2: "stream", 3: "dmma"}[info.batched_path],
                     single_path="low-latency" if info.single_path == 1 else "generic",
                     cluster_size=info.cluster_size, macs_per_eval=info.macs_per_eval,
                     kernel_launches=info.kernel_launches, sm_count=info.sm_count)

@@ -87,7 +87,8 @@ typedef struct {
 typedef struct {
     int32_t precision_single;             /* resolved ANNF_PREC_* of annf_eval_openmm */
     int32_t precision_batched;            /* resolved ANNF_PREC_* of annf_eval_batched */
-    int32_t batched_path;                 /* 0 generic fused per-CTA kernel, 1 layer-wise tensor-core path, 2 fused kernel with TMA-streamed weights */
+    int32_t batched_path;                 /* 0 generic fused per-CTA kernel, 1 layer-wise tensor-core path, 2 fused kernel with TMA-streamed weights,
+                                           * 3 the same on the FP64 tensor path (DMMA) */
     int32_t cluster_size;                 /* CTAs per cluster of the single-replica kernel */
     int64_t macs_per_eval;                /* M = sum n_l * n_{l+1} */
     int64_t kernel_launches;              /* kernels launched through this handle since creation */

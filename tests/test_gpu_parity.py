@@ -457,7 +457,7 @@ def test_default_kernel_selection():
     kernel = CalcANNForce()
     kernel.initialize(7, force)
     info = kernel.info()
-    assert info["single_path"] == "low-latency" and info["batched_path"] == "stream"
+    assert info["single_path"] == "low-latency" and info["batched_path"] == "dmma"
     pairs = _pair_force(10, 6, seed=3)
     kernel = CalcANNForce()
     kernel.initialize(10, pairs)
@@ -501,23 +501,23 @@ def test_streamed_kernel_every_tile_size(tile, precision, e_tol, f_tol, monkeypa
         pos = synthetic.make_positions(n_atoms, R, seed=R)
         cen = synthetic.make_centers(force, R, seed=R + 1)
         e, f, kernel = run_batched(force, pos, cen, precision=precision)
-        assert kernel.info()["batched_path"] == "stream"
+        assert kernel.info()["batched_path"] == "stream"      # ANNF_STREAM_TR selects the FMA variant of the streamed kernel
         e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
         np.testing.assert_allclose(e, e_ref, rtol=e_tol)
         assert max_norm_rel(f, f_ref) <= f_tol
 
 
 def test_streamed_kernel_unaligned_coordinates_and_wide_layers():
-    """Coordinates that start at an address that is not 16-byte aligned take the gather path; layers wider than
-    512 nodes give every warp two 32-node chunks and no K-split."""
-    force = synthetic.make_force([21, 600, 70, 2], ["Tanh", "Linear", "Tanh"], 7, seed=8)
+    """Coordinates that start at an address that is not 16-byte aligned take the gather path; a 400-node layer gives
+    every warp four 8-node tiles."""
+    force = synthetic.make_force([21, 400, 70, 2], ["Tanh", "Linear", "Tanh"], 7, seed=8)
     R = 19
     pos = synthetic.make_positions(7, R + 1, seed=9).astype(np.float32)
     flat = torch.as_tensor(pos.reshape(-1), device="cuda")
     coords = flat[21:].view(R, 7, 3)              # 84-byte offset
     kernel = CalcANNForce(precision="fp64")
     kernel.initialize(7, force)
-    assert kernel.info()["batched_path"] == "stream"
+    assert kernel.info()["batched_path"] == "dmma"
     e, f = kernel.execute_batched(coords)
     torch.cuda.synchronize()
     e_ref, f_ref = port.evaluate(force, pos[1:].astype(np.float64))

@@ -15,9 +15,13 @@ for cfg in ("c3", "c4"):
     buf = (C.c_int64 * 64)()
     _capi.check(_capi.lib().annf_debug_stream_phases(k._handle, buf))
     L = len(c["nodes"]); npass = 2 * (L - 1)
+    if len(sys.argv) > 1:
+        import time
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(200): k.execute_batched(coords, cen)
+        torch.cuda.synchronize(); print(cfg, "us per call (stream of 200):", 1e6 * (time.perf_counter() - t0) / 200)
     t = np.array(buf[:5 + npass])
     names = ["prologue", "features"] + ["fwd%d" % l for l in range(L - 1)] + ["head"] + ["bwd%d" % l for l in range(L - 2, -1, -1)] + ["forces"]
     order = [0, 1, 2] + [3 + p for p in range(L - 1)] + [3 + npass] + [3 + p for p in range(L - 1, npass)] + [4 + npass]
     ts = t[order]
     print(cfg, k.info()["batched_path"], dict(zip(names, np.diff(ts).tolist())), "total", int(ts[-1] - ts[0]))
-    print(cfg, "  waited for weights per pass", list(buf[32:32 + npass]), "epilogue per pass", list(buf[48:48 + npass]))
