@@ -612,6 +612,20 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
     }
     const size_t row = (size_t) atoms_per_replica * 3;
     const bool zero_fill = h->net.n_sel != atoms_per_replica;   // kernels write the selected atoms only
+    if (chunks == 1) {
+        // small batches: nothing to overlap, so one stream and one wait (the pipelined path costs ~6 stream / event calls more)
+        cudaStream_t s = h->host_stream;
+        ANNF_CUDA(cudaMemcpyAsync(h->h_coords, coords_host, sizeof(float) * n_coords, cudaMemcpyHostToDevice, s));
+        if (centers_host) ANNF_CUDA(cudaMemcpyAsync(h->h_centers, centers_host, sizeof(float) * n_centers, cudaMemcpyHostToDevice, s));
+        if (zero_fill) ANNF_CUDA(cudaMemsetAsync(h->h_forces, 0, sizeof(float) * n_coords, s));
+        annf_status st = annf_eval_batched(h, R, h->h_coords, atoms_per_replica, centers_host ? h->h_centers : nullptr, h->h_forces,
+                                           h->h_energies, s);
+        if (st != ANNF_OK) { cudaStreamSynchronize(s); return st; }
+        ANNF_CUDA(cudaMemcpyAsync(forces_host, h->h_forces, sizeof(float) * n_coords, cudaMemcpyDeviceToHost, s));
+        ANNF_CUDA(cudaMemcpyAsync(energies_host, h->h_energies, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
+        ANNF_CUDA(cudaStreamSynchronize(s));
+        return ANNF_OK;
+    }
     // Chunk sizes DEcrease (weights chunks+1, chunks, ..., 2): the copy-in stream is the long pole, so what remains after
     // its last byte lands — evaluating and copying out the LAST chunk — should be as short as possible.
     int bounds[9];

@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
                     help="replay the step from a CUDA graph (auto: on for the launch-bound workloads c2/c3/c4)")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the short runs of the other BASELINE shapes that the default (c5, 1 GPU) line carries")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -390,6 +392,23 @@ def main():
                        api=out["path"], note="OpenMM keeps positions and forces on the device: no host traffic per step")
         except Exception as exc:       # noqa: BLE001
             e2e["error"] = str(exc)[:200]
+        # the legacy CUDA plugin cannot be built (OpenMM absent); tools/legacy_restatement.cu restates the kernel it
+        # generates for the only network class it supports (3 layers, Tanh / Linear: C1's 21-40-2), clearly labelled
+        legacy = os.path.join(ROOT, "tools", "_build", "legacy_restatement")
+        try:
+            import subprocess
+            if os.path.exists(legacy) and os.path.exists(exe):
+                leg = json.loads(subprocess.run([legacy, "20000"], check=True, capture_output=True, text=True, timeout=120).stdout)
+                ours = json.loads(subprocess.run([exe, "20000", "c1"], check=True, capture_output=True, text=True, timeout=120).stdout)
+                e2e["vs_legacy_restatement_c1"] = dict(
+                    what=leg["what"], network=leg["network"],
+                    legacy_us_per_step_stream=leg["us_per_step_stream"], legacy_us_per_step_graph=leg["us_per_step_graph"],
+                    ours_us_per_step_stream=ours["gpu_us_per_step"], ours_us_per_step_graph=ours["graph_us_per_step"],
+                    speedup_stream=leg["us_per_step_stream"] / ours["gpu_us_per_step"],
+                    speedup_graph=leg["us_per_step_graph"] / ours["graph_us_per_step"],
+                    note="both are bound by kernel launch + a chain of dependent layers; ours runs fp64, the legacy scheme fp32")
+        except Exception as exc:       # noqa: BLE001
+            e2e["legacy_error"] = str(exc)[:200]
 
     # optional replica-exchange all-gather of energies (outside the timed force path)
     exchange_us = None
@@ -417,30 +436,63 @@ def main():
         name, rec = dominant
         avg_ms = rec["total_ms"] / max(rec["launches"], 1)
         kflops = kernel_flops(name, nodes, R, flops_eval)
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        if name.startswith("gemm["):
+            # tcgen05 kind::tf32 path (3xTF32): dense TF32 peak
+            peak = peaks["bf16_tflops_sustained"] / 2.0
+            peak_source = ("%s bf16_tflops_sustained / 2 (dense TF32 = half the bf16 rate; a 3xTF32 kernel tops out at frac 1/3)"
+                           % peaks["source"])
+        elif "f32" in name:
+            clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
+            peak = 128.0 * 2.0 * info["sm_count"] * clk / 1e12
+            peak_source = "FP32 FMA pipe: 128 FMA/clk/SM x %d SMs x %.0f MHz" % (info["sm_count"], clk / 1e6)
+        else:
+            # fp64 kernels: the FP64 pipe.  DFMA and DMMA (mma.sync.m8n8k4.f64) both issue at 64 FMA/clk/SM on B200
+            # (measured with tools/fp64_probe.cu, profiles/r01_fp64_probe.txt); peak = 64 x 2 x SMs x SM clock under load
+            clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
+            peak = 64.0 * 2.0 * info["sm_count"] * clk / 1e12
+            peak_source = "FP64 pipe: 64 FMA/clk/SM (tools/fp64_probe.cu, profiles/r01_fp64_probe.txt) x %d SMs x %.0f MHz" % (
+                info["sm_count"], clk / 1e6)
         achieved = kflops / (avg_ms * 1e-3) / 1e12
-        roofline = dict(bound="tensor", kernel=name, achieved=achieved, peak=tf32_peak, unit="TFLOP/s",
-                        frac=achieved / tf32_peak, traffic=load_traffic(name),
+        roofline = dict(bound="tensor", kernel=name, achieved=achieved, peak=peak, unit="TFLOP/s",
+                        frac=achieved / peak, traffic=load_traffic(name),
                         avg_launch_ms=avg_ms, launches=rec["launches"],
                         share_of_step=rec["total_ms"] / max(sum(v["total_ms"] for v in times.values()), 1e-12),
-                        algorithmic_flops_per_launch=kflops,
-                        peak_source="%s bf16_tflops_sustained / 2 (dense TF32 = half the bf16 rate; a 3xTF32 kernel tops out at frac 1/3)"
-                                    % peaks["source"],
+                        algorithmic_flops_per_launch=kflops, peak_source=peak_source,
+                        note=(None if args.workload == "c5" else
+                              "latency-bound shape: a launch is a chain of dependent layers; the fraction is reported for information"),
                         kernels={k: dict(launches=v["launches"], avg_ms=v["total_ms"] / max(v["launches"], 1)) for k, v in times.items()})
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         _, _, _, cpu = cpu_reference(args.workload, force, atoms, 15.0)
 
+    # the other BASELINE shapes, measured in the same run (short): one sub-process each, their own full line is
+    # available with --workload
+    others = None
+    if world == 1 and args.workload == "c5" and not args.no_others and args.impl == "ours":
+        import subprocess
+        others = {}
+        for w in ("c2", "c3", "c4"):
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", w, "--no-cpu-baseline", "--no-others"],
+                                     check=True, capture_output=True, text=True, timeout=300).stdout.strip().splitlines()[-1]
+                d = json.loads(out)
+                others[w] = dict(workload=d["config"]["workload"], value=d["value"], unit=d["unit"], us_per_step=1e3 * d["ms_per_step"],
+                                 path=d["config"]["path"], dtype=d["dtype"], e2e=d["e2e"],
+                                 roofline=dict(kernel=d["roofline"]["kernel"], frac=d["roofline"]["frac"], peak=d["roofline"]["peak"],
+                                               achieved=d["roofline"]["achieved"]) if d.get("roofline") else None)
+            except Exception as exc:       # noqa: BLE001
+                others[w] = dict(error=str(exc)[:200])
+
     steps_per_s_per_replica = steps / (gpu_ms_max * 1e-3)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=gpu_ms_max / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"fp64": "f64", "fp32": "f32", "tf32x3": "tf32x3 (fp32 accumulate)"}[info["precision_single" if single else "precision_batched"]],
-                data="synthetic", config=dict(config, l2=l2_policy, path=info["batched_path"] if not single else "single-replica cluster kernel",
+                data="synthetic", config=dict(config, l2=l2_policy, path=info["batched_path"] if not single else "single-replica kernel (%s)" % info["single_path"],
                                               wall_ms_per_step=1e3 * wall / steps),
                 clocks=sampler.summary(), e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                 ns_per_day_per_replica=steps_per_s_per_replica * TIMESTEP_FS * 1e-6 * 86400.0,
-                exchange_allgather_us=exchange_us)
+                exchange_allgather_us=exchange_us, other_workloads=others)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
