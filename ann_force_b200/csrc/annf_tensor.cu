@@ -10,8 +10,8 @@
 // Weights are split once at plan creation (both W and W^T, K-major for the tensor core); activations
 // are split by the epilogue that produces them.  The tiny output layer, the umbrella energy and its
 // gradient stay fp64 in a SIMT "head" kernel; gather/centre ("prep") is a bandwidth-bound SIMT kernel;
-// the centring Jacobian is one mean per component, computed ahead of the last backward contraction
-// ("colmean"), whose epilogue then writes the forces directly.
+// the Jacobian of "divide by s, subtract the centroid" is folded into the backward copy of the first connection at plan
+// creation, so the last backward contraction's accumulator is the force and its epilogue writes it straight out.
 //
 // GEMM kernel anatomy (one 128 x BN output tile per CTA, BN = 128 or 256):
 //   epilogue warps (BN/32 of them, first): tcgen05.ld TMEM -> registers -> bias / tanh / tanh' -> hi/lo or force stores
@@ -63,9 +63,7 @@ struct GemmParams {
     float* out_hi;                    // [M][ld_out]  (EPI_STORE: the plain fp32 result; EPI_FORCE: forces [M][atoms][3])
     float* out_lo;
     int ld_out;                       //              (EPI_FORCE: 3 * atoms_per_replica)
-    const float* row_mean;            // [M][4] mean input-gradient per component (EPI_FORCE)
     const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
-    float neg_inv_scale;              // -1 / scaling_factor (EPI_FORCE)
     int dry;                          // experiments (ANNF_TENSOR_DRY=1): return immediately, to measure the launch floor
 };
 
@@ -206,9 +204,7 @@ __device__ __forceinline__ EpiAux epilogue_load(const GemmParams& p, int m, int 
     EpiAux x;
     x.a = make_float4(0.f, 0.f, 0.f, 0.f);
     x.b = x.a;
-    if (p.epi == EPI_FORCE) {
-        x.a = __ldg(reinterpret_cast<const float4*>(p.row_mean) + m);
-    } else if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
+    if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
         x.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     } else if (p.epi == EPI_TANH_GRAD) {
         x.a = __ldg(reinterpret_cast<const float4*>(p.aux_hi + (size_t) m * p.ld_aux + n));
@@ -223,15 +219,10 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
         return;
     }
     if (p.epi == EPI_FORCE) {
-        // column n = 3 * atom + component: F = -(g - mean_component) / s = g * (-1/s) + mean_component / s
-        // (ANN_ReferenceKernels.cpp:397-410, the O(A^2) Jacobian loop collapsed into one mean per component)
-        const float4 mu = x.a;
-        const float k = p.neg_inv_scale;
-        const int c0 = n % 3;                                   // component of the first of the four columns
-        const float ma = -k * (c0 == 0 ? mu.x : (c0 == 1 ? mu.y : mu.z));      // mean/s for column n, n+3
-        const float mb = -k * (c0 == 0 ? mu.y : (c0 == 1 ? mu.z : mu.x));      // ... n+1
-        const float mc = -k * (c0 == 0 ? mu.z : (c0 == 1 ? mu.x : mu.y));      // ... n+2
-        const float4 f = make_float4(fmaf(v.x, k, ma), fmaf(v.y, k, mb), fmaf(v.z, k, mc), fmaf(v.w, k, ma));
+        // column n = 3 * atom + component.  The B operand of this GEMM is W0c^T = -(1/s) (W_0 - (1/A) sum_i W_0[.][3i+c])^T, the
+        // first connection with the Jacobian of "divide by s, subtract the centroid" folded in at plan creation
+        // (ANN_ReferenceKernels.cpp:137-145, :397-410), so the accumulator already IS the force.
+        const float4 f = v;
         float* row = p.out_hi + (size_t) m * p.ld_out;
         if (p.sel_atoms == nullptr) {
             *reinterpret_cast<float4*>(row + n) = f;
@@ -601,6 +592,9 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
 // backward contraction through the output connection, fused with act'() of the last hidden layer.
 // One 128-thread CTA per replica: every thread owns hidden units tid, tid+128, ... so the dependent
 // chains are short; the nL output sums are reduced with shuffles + one shared-memory hop.
+// (Tried and rejected on measurement: a warp-per-replica variant, 8 replicas per CTA with the output connection staged in
+// shared memory.  Fully unrolled it was instruction-fetch bound — 58 % stall_no_inst, ~170 cycles per 128-byte line of code
+// that runs once per CTA; rolled, its 128 fat CTAs delayed the cluster GEMM that follows under PDL: step 110 -> 121 us.)
 constexpr int kHeadThreads = 128;
 constexpr int kHeadMaxOut = 64;
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, const float* __restrict__ centers,
@@ -696,51 +690,6 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     }
 }
 
-// colmean: mean over atoms of the input gradient, per replica and component, WITHOUT forming the gradient:
-//   (1/A) sum_i g[3i+c] = (1/A) sum_k D1[k] * (sum_i W0[k][3i+c])     (wsum precomputed at plan creation)
-// This is the Jacobian term of centroid removal (ANN_ReferenceKernels.cpp:402-406); knowing it before the last
-// backward contraction lets that GEMM's epilogue write the forces directly.  One 128-thread CTA per replica.
-__global__ void __launch_bounds__(128) colmean_kernel(int R, int K, int A, const float* __restrict__ d_hi,
-                                                     const float* __restrict__ d_lo, int ld, const double* __restrict__ wsum,
-                                                     float* __restrict__ row_mean) {
-    pdl_launch_dependents();
-    pdl_wait();
-    if (R < 0) return;                                      // experiments: launch-floor dry run
-    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ double part[4][3];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int kb = tid; kb < K; kb += 4 * 128) {             // four terms per pass, every load issued before the math
-        float dh[4], dl[4];
-        double w0[4], w1[4], w2[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const int k = kb + v * 128;
-            const bool in = k < K;
-            dh[v] = in ? __ldg(d_hi + (size_t) r * ld + k) : 0.f;
-            dl[v] = in ? __ldg(d_lo + (size_t) r * ld + k) : 0.f;
-            w0[v] = in ? __ldg(wsum + k) : 0.0;
-            w1[v] = in ? __ldg(wsum + K + k) : 0.0;
-            w2[v] = in ? __ldg(wsum + 2 * K + k) : 0.0;
-        }
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const double d = (double) (dh[v] + dl[v]);
-            s0 = fma(d, w0[v], s0);
-            s1 = fma(d, w1[v], s1);
-            s2 = fma(d, w2[v], s2);
-        }
-    }
-    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; }
-    __syncthreads();
-    if (tid == 0) {
-        const double t0 = (part[0][0] + part[1][0]) + (part[2][0] + part[3][0]);
-        const double t1 = (part[0][1] + part[1][1]) + (part[2][1] + part[3][1]);
-        const double t2 = (part[0][2] + part[1][2]) + (part[2][2] + part[3][2]);
-        *reinterpret_cast<float4*>(row_mean + (size_t) r * 4) = make_float4((float) (t0 / A), (float) (t1 / A), (float) (t2 / A), 0.f);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Host side: plan
 // ------------------------------------------------------------------------------------------------
@@ -787,7 +736,7 @@ constexpr int kPlanSlots = 2;         // independent activation-buffer sets: two
 struct PlanSlot {
     int cap = 0;                                    // replica capacity of the activation buffers
     // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as TF32 pairs
-    float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {}, *row_mean = nullptr;
+    float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {};
     std::vector<GemmOp> fwd, bwd;
 };
 
@@ -800,7 +749,6 @@ struct TensorPlan {
     // weights (TF32 pairs), forward [n_{l+1}][ld(n_l)] and transposed [n_l][ld(n_{l+1})], l = 0..L-3
     float *w_hi[kMaxLayers] = {}, *w_lo[kMaxLayers] = {}, *wt_hi[kMaxLayers] = {}, *wt_lo[kMaxLayers] = {}, *bias[kMaxLayers] = {};
     PlanSlot slots[kPlanSlots];
-    double* wsum = nullptr;                         // [3][n_1]: sum over atoms of W_0[k][3i+c]
     bool sel_identity = false;                      // selection is atoms 0..A-1 in order
     int force_bn = 0;                               // ANNF_GEMM_BN=128|256 (1-CTA tiles) or 512 (CTA pairs) overrides the tile heuristic
     int force_split = 0;                            // ANNF_GEMM_SPLIT_SHORTK=1|2|4|8 overrides split-K for GEMMs with K <= 1024
@@ -813,8 +761,6 @@ static void free_activations(PlanSlot* t) {
         cudaFree(t->x_hi[l]); cudaFree(t->x_lo[l]); cudaFree(t->d_hi[l]); cudaFree(t->d_lo[l]);
         t->x_hi[l] = t->x_lo[l] = t->d_hi[l] = t->d_lo[l] = nullptr;
     }
-    cudaFree(t->row_mean);
-    t->row_mean = nullptr;
     t->cap = 0;
 }
 
@@ -824,7 +770,6 @@ void tensor_plan_destroy(TensorPlan* t) {
     for (int l = 0; l < kMaxLayers; l++) {
         cudaFree(t->w_hi[l]); cudaFree(t->w_lo[l]); cudaFree(t->wt_hi[l]); cudaFree(t->wt_lo[l]); cudaFree(t->bias[l]);
     }
-    cudaFree(t->wsum);
     delete t;
 }
 
@@ -883,28 +828,24 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     for (int l = 0; l + 2 < L; l++) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
         std::vector<float> w((size_t) n_out * t->ld[l], 0.f), wt((size_t) n_in * t->ld[l + 1], 0.f);
-        for (int j = 0; j < n_out; j++)
+        for (int j = 0; j < n_out; j++) {
+            // l == 0: the backward copy carries the centring / scaling Jacobian (see EPI_FORCE), folded in fp64
+            double wsum[3] = {0.0, 0.0, 0.0};
+            if (l == 0)
+                for (int i = 0; i < n_in; i++) wsum[i % 3] += coeff[0][(size_t) j * n_in + i];
             for (int i = 0; i < n_in; i++) {
-                const float v = (float) coeff[l][(size_t) j * n_in + i];
-                w[(size_t) j * t->ld[l] + i] = v;
-                wt[(size_t) i * t->ld[l + 1] + j] = v;
+                const double v = coeff[l][(size_t) j * n_in + i];
+                w[(size_t) j * t->ld[l] + i] = (float) v;
+                wt[(size_t) i * t->ld[l + 1] + j] = l == 0 ? (float) (-(v - wsum[i % 3] / net.n_sel) / net.scale) : (float) v;
             }
+        }
         if (upload_pair(w, &t->w_hi[l], &t->w_lo[l]) != cudaSuccess || upload_pair(wt, &t->wt_hi[l], &t->wt_lo[l]) != cudaSuccess) {
             tensor_plan_destroy(t);
             return no("out of device memory for the tensor-core weight copies");
         }
     }
     // fp32 biases live in NetView::b32 already
-    {   // per-component column sums of W_0 for the centring Jacobian (colmean_kernel)
-        const int n0 = net.nodes[0], n1 = net.nodes[1];
-        std::vector<double> wsum((size_t) 3 * n1, 0.0);
-        for (int k = 0; k < n1; k++)
-            for (int i = 0; i < n0; i++) wsum[(size_t) (i % 3) * n1 + k] += coeff[0][(size_t) k * n0 + i];
-        if (cudaMalloc((void**) &t->wsum, sizeof(double) * wsum.size()) != cudaSuccess ||
-            cudaMemcpy(t->wsum, wsum.data(), sizeof(double) * wsum.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-            tensor_plan_destroy(t);
-            return no("out of device memory");
-        }
+    {
         std::vector<int> sel(net.n_sel);
         cudaMemcpy(sel.data(), net.sel_atoms, sizeof(int) * net.n_sel, cudaMemcpyDeviceToHost);
         t->sel_identity = true;
@@ -930,7 +871,6 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_hi[l], plan->ld[l]);
         if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], plan->ld[l]);
     }
-    if (err == cudaSuccess) err = alloc(&t->row_mean, 4);
     if (err != cudaSuccess) return err;
     t->cap = cap;
     t->fwd.clear();
@@ -959,8 +899,6 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         op.p.N = N; op.p.K = K;
         if (l == 0) {
             op.p.epi = EPI_FORCE;                     // out_hi / ld_out / sel_atoms are per call (launch_gemm)
-            op.p.row_mean = t->row_mean;
-            op.p.neg_inv_scale = (float) (-1.0 / net.scale);
         } else {
             op.p.epi = plan->types[l - 1] == ANNF_TANH ? EPI_TANH_GRAD : EPI_LINEAR_GRAD;
             op.p.aux_hi = t->x_hi[l]; op.p.aux_lo = t->x_lo[l]; op.p.ld_aux = plan->ld[l];
@@ -1121,13 +1059,6 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : sl->bwd) {
-        if (op.p.epi == EPI_FORCE) {
-            err = timed("colmean_kernel", [&] {
-                return launch_pdl(colmean_kernel, dim3(R), dim3(128), 0, stream, 1, 0, t->dry ? -R : R, t->nodes[1], net.n_sel, (const float*) sl->d_hi[1],
-                                  (const float*) sl->d_lo[1], t->ld[1], (const double*) t->wsum, sl->row_mean);
-            });
-            if (err != cudaSuccess) return err;
-        }
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
         err = timed(name, [&] { return launch_gemm(t, op, R, stream, net, forces, atoms_per_replica); });
         if (err != cudaSuccess) return err;
