@@ -30,8 +30,8 @@ namespace annf {
 constexpr int kDWarps = 16;
 constexpr int kDComputeThreads = 32 * kDWarps;
 constexpr int kDThreads = kDComputeThreads + 32;      // + one producer warp
-constexpr int kDStages = 3;
-constexpr int kDStageBytes = 32 * 1024;
+constexpr int kDStages = 2;
+constexpr int kDStageBytes = 64 * 1024;
 constexpr int kDTile = 8;                             // replicas per CTA = rows of the DMMA A operand
 constexpr int kDMaxNT = 4;                            // node tiles (of 8) per warp
 

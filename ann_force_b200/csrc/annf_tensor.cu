@@ -152,7 +152,7 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kThreads = (kEpiWarps + 4) * 32;                       // + producer warp, MMA warp, 2 idle (warpgroup padding)
     static constexpr int kBRows = BN / CG;                                      // rows of B this CTA stages
     static constexpr int kStageBytes = (2 * BM + 2 * kBRows) * BK * 4;
-    static constexpr int kStages = kStageBytes > 80 * 1024 ? 2 : 3;
+    static constexpr int kStages = kStageBytes > 80 * 1024 ? 2 : (kStageBytes > 48 * 1024 ? 3 : 4);
     static constexpr int kStagingLd = BN + 4;                                   // fp32 elements, padded against bank conflicts
     static constexpr int kStagingBytes = BM * kStagingLd * 4;
     static constexpr int kDataBytes = kStageBytes * kStages > kStagingBytes ? kStageBytes * kStages : kStagingBytes;
@@ -316,6 +316,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     constexpr int kColsPerWarp = 128;                       // accumulator columns held in registers by one epilogue thread
     constexpr int kEpiThreads = BN >= 256 ? 32 * kEpiWarps : Cfg::kThreads;   // threads sharing the cooperative epilogue
     constexpr int kBRows = Cfg::kBRows;
+    constexpr int kBBox = kBRows < 128 ? kBRows : 128;      // rows of one TMA box of B (the 256 x 128 pair tile stages 64 per CTA)
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms (TMA and UMMA must agree on address bits 7..9)
     unsigned char* data = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -396,18 +397,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         tma_load_2d_pair(base, &tm_a_hi, full_leader, kc, m0);
                         tma_load_2d_pair(base + BM * BK * 4, &tm_a_lo, full_leader, kc, m0);
 #pragma unroll
-                        for (int h = 0; h < kBRows / 128; h++) {
-                            tma_load_2d_pair(base + 2 * BM * BK * 4 + h * 128 * BK * 4, &tm_b_hi, full_leader, kc, b_row0 + h * 128);
-                            tma_load_2d_pair(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * 128 * BK * 4, &tm_b_lo, full_leader, kc, b_row0 + h * 128);
+                        for (int h = 0; h < kBRows / kBBox; h++) {
+                            tma_load_2d_pair(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
+                            tma_load_2d_pair(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
                         }
                     } else {
                         mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
                         tma_load_2d(base, &tm_a_hi, full, kc, m0);
                         tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
 #pragma unroll
-                        for (int h = 0; h < kBRows / 128; h++) {                  // TMA boxes are at most 256 rows; use 128-row boxes
-                            tma_load_2d(base + 2 * BM * BK * 4 + h * 128 * BK * 4, &tm_b_hi, full, kc, b_row0 + h * 128);
-                            tma_load_2d(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * 128 * BK * 4, &tm_b_lo, full, kc, b_row0 + h * 128);
+                        for (int h = 0; h < kBRows / kBBox; h++) {                // TMA boxes are at most 256 rows; use 128-row boxes
+                            tma_load_2d(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full, kc, b_row0 + h * kBBox);
+                            tma_load_2d(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full, kc, b_row0 + h * kBBox);
                         }
                     }
                 }
@@ -727,6 +728,7 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct GemmOp {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap b_hi64, b_lo64;          // the same B with 64-row boxes (256 x 128 CTA-pair tiles)
     GemmParams p;
     char name[48];
 };
@@ -880,7 +882,8 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         memset(&op, 0, sizeof(op));
         const int K = plan->nodes[l], N = plan->nodes[l + 1];
         bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, plan->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, plan->ld[l], BM) &&
-                  make_map(&op.b_hi, plan->w_hi[l], N, K, plan->ld[l], 128) && make_map(&op.b_lo, plan->w_lo[l], N, K, plan->ld[l], 128);
+                  make_map(&op.b_hi, plan->w_hi[l], N, K, plan->ld[l], 128) && make_map(&op.b_lo, plan->w_lo[l], N, K, plan->ld[l], 128) &&
+                  make_map(&op.b_hi64, plan->w_hi[l], N, K, plan->ld[l], 64) && make_map(&op.b_lo64, plan->w_lo[l], N, K, plan->ld[l], 64);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
         op.p.epi = plan->types[l] == ANNF_TANH ? EPI_BIAS_TANH : EPI_BIAS_LINEAR;
@@ -894,7 +897,8 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         memset(&op, 0, sizeof(op));
         const int K = plan->nodes[l + 1], N = plan->nodes[l];
         bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM) &&
-                  make_map(&op.b_hi, plan->wt_hi[l], N, K, plan->ld[l + 1], 128) && make_map(&op.b_lo, plan->wt_lo[l], N, K, plan->ld[l + 1], 128);
+                  make_map(&op.b_hi, plan->wt_hi[l], N, K, plan->ld[l + 1], 128) && make_map(&op.b_lo, plan->wt_lo[l], N, K, plan->ld[l + 1], 128) &&
+                  make_map(&op.b_hi64, plan->wt_hi[l], N, K, plan->ld[l + 1], 64) && make_map(&op.b_lo64, plan->wt_lo[l], N, K, plan->ld[l + 1], 64);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
         if (l == 0) {
@@ -952,8 +956,9 @@ static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStre
         configured[dev] = true;
     }
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM * CG - 1) / (BM * CG);
+    constexpr bool kBox64 = Cfg::kBRows < 128;
     return launch_pdl(gemm3x_kernel<BN, S, CG>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG, S,
-                      op.a_hi, op.a_lo, op.b_hi, op.b_lo, p);
+                      op.a_hi, op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo, p);
 }
 
 static int pick_split(int tiles, int k_blocks, int sm_count) {
@@ -987,6 +992,18 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         // 8-way DSMEM reduce of 128 KB partials lose).  So: CTA pairs when they fill the machine WITHOUT splitting K.
         if (p.N >= 256 && s2 == 1 && pair_ctas >= t->sm_count / 2) mode = 512;
         else mode = (tiles128 > t->sm_count && pick_split(tiles128, kb, t->sm_count) == 1) ? 256 : 128;
+    }
+    if (mode == 130) {
+        // 256 x 128 tiles on CTA pairs: each CTA stages its own 128 rows of A and 64 of the 128 rows of B (48 KB per K-block
+        // instead of 64), split along K inside the same cluster (2 x S CTAs, S <= 4 keeps the cluster portable)
+        const int pair_ctas = 2 * ((p.N + 127) / 128) * ((R + 255) / 256);
+        int s = std::min(4, pick_split(pair_ctas, kb, t->sm_count));
+        if (t->force_split > 0 && kb <= 32) s = std::min(4, t->force_split);
+        switch (s) {
+        case 4: return launch_gemm_t<128, 4, 2>(op, p, stream);
+        case 2: return launch_gemm_t<128, 2, 2>(op, p, stream);
+        default: return launch_gemm_t<128, 1, 2>(op, p, stream);
+        }
     }
     if (mode == 512) {
         const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);

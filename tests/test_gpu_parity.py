@@ -279,7 +279,7 @@ def test_tensor_core_path_matches_oracle(nodes, types, R):
     np.testing.assert_array_equal(f, f2)
 
 
-@pytest.mark.parametrize("bn", ["128", "256", "512"])
+@pytest.mark.parametrize("bn", ["128", "256", "512", "130"])
 def test_tensor_core_tile_widths_agree(bn, monkeypatch):
     """Every GEMM tile shape against the oracle — 128 wide (4 epilogue warps), 256 wide (8 epilogue warps + setmaxnreg)
     and "512" = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, multicast commits) — with split-K 4 and 8,
