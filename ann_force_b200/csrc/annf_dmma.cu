@@ -214,8 +214,17 @@ __device__ __forceinline__ void dmma_pass(PassCtx& ctx, int p, int mode, int typ
         for (int q = 0; q < kDMaxNT; q++) {
             if (q < NT) {
                 const int j = (tile0 + q) * 8 + jl;
-                if (j < n_lane) epi(j, r, c[0][q][0] + c[1][q][0]);
-                if (j + 1 < n_lane) epi(j + 1, r, c[0][q][1] + c[1][q][1]);
+                const double v0 = c[0][q][0] + c[1][q][0], v1 = c[0][q][1] + c[1][q][1];
+                if (mode == kFwdHidden && type == ANNF_TANH) {
+                    // the lane's two tanh chains (~25 dependent fp64 instructions each) side by side, stores predicated;
+                    // bias rows are padded, so b[j + 1] is readable
+                    const double t0 = annf_tanh(v0 + b[j]), t1 = annf_tanh(v1 + b[j + 1]);
+                    if (j < n_lane) out[j * kDTile + r] = t0;
+                    if (j + 1 < n_lane) out[(j + 1) * kDTile + r] = t1;
+                } else {
+                    if (j < n_lane) epi(j, r, v0);
+                    if (j + 1 < n_lane) epi(j + 1, r, v1);
+                }
             }
         }
     }
