@@ -192,6 +192,18 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask) : "memory");
 }
+// 1-CTA MMAs, but the completion is signalled in every CTA of `cta_mask` (CTAs that share multicast operand tiles)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// TMA load whose box lands at the same shared-memory offset, and completes its bytes on the mbarrier at the same offset, in
+// every CTA of `cta_mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (m >> 4) << 24);
 }
@@ -252,17 +264,17 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
 // Cooperative epilogue over the parked tile(s): thread t of kGroupThreads walks (row, 4-column) groups with consecutive lanes
 // along a row — 512-byte coalesced global accesses — summing the S split-K partials (own + peers', through DSMEM) in a fixed
 // order, with the auxiliary global loads of four groups issued ahead of the dependent math.
-template <int BN, int S, int CG, int kGroupThreads>
+template <int BN, int S, int CG, int kGroupThreads, int CX = CG>
 __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
     using Cfg = GemmCfg<BN, CG>;
-    constexpr int kRows = BM / S;                                                  // rows this CTA finishes
+    constexpr int kRows = (BM + S - 1) / S;                                        // rows this CTA finishes (S = 3: 43, 43, 42)
     constexpr int kVecPerRow = BN / 4;
     float* staging = reinterpret_cast<float*>(data);
     const float* peer[S];
     if (S > 1) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
-        for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, pair_rank + CG * r);   // same pair position, split r
+        for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, pair_rank + CX * r);   // same x position, split r
     } else {
         peer[0] = staging;
     }
@@ -279,7 +291,7 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsign
             const int v = t + (g0 + u) * kGroupThreads;
             const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
             mm[u] = m0 + row; nn[u] = n0 + col;
-            ok[u] = (g0 + u) < kGroups && v < kRows * kVecPerRow && mm[u] < p.M && nn[u] < p.N;
+            ok[u] = (g0 + u) < kGroups && v < kRows * kVecPerRow && row < BM && mm[u] < p.M && nn[u] < p.N;
             sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok[u]) {
                 aux[u] = epilogue_load(p, mm[u], nn[u]);
@@ -306,7 +318,10 @@ template <bool kCluster> __device__ __forceinline__ void role_sync() {
     }
 }
 
-template <int BN, int S, int CG>
+// NX = 2 (1-CTA tiles only): the two CTAs at x = 2i, 2i + 1 of a cluster compute neighbouring N tiles of the SAME rows, so
+// they need the same A tile: each loads half of its rows and TMA-multicasts them into both CTAs (48 instead of 64 KB of
+// L2 -> SM traffic per K-block and CTA).  A stage is free again when BOTH CTAs' MMAs have retired (multicast commit).
+template <int BN, int S, int CG, int NX = 1>
 __global__ void __launch_bounds__(GemmCfg<BN, CG>::kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmParams p) {
@@ -329,12 +344,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair_rank = CG == 2 ? (int) (blockIdx.x & 1) : 0;                   // 0 = leader of the CTA pair
+    static_assert(NX == 1 || (CG == 1 && NX == 2), "operand multicast is implemented for pairs of 1-CTA tiles");
+    constexpr int CX = CG * NX;                                                   // cluster extent along x
+    const int x_rank = CX == 2 ? (int) (blockIdx.x & 1) : 0;                      // position in the cluster along x
+    const int pair_rank = CG == 2 ? x_rank : 0;                                   // 0 = leader of the CTA pair
     const int n0 = (CG == 2 ? (int) (blockIdx.x >> 1) : (int) blockIdx.x) * BN;   // first output column of the tile
     const int m0 = (CG == 2 ? (int) blockIdx.y * 2 + pair_rank : (int) blockIdx.y) * BM;
     const int b_row0 = n0 + pair_rank * kBRows;                                   // first row of B this CTA stages
     const int rank = S > 1 ? (int) blockIdx.z : 0;                                // split-K index
-    const uint32_t my_cta = (CG == 2 || S > 1) ? cluster_ctarank() : 0u;
+    const uint32_t my_cta = (CX == 2 || S > 1) ? cluster_ctarank() : 0u;
+    const uint16_t mc_mask = (uint16_t) (3u << (my_cta & ~1u));                   // NX = 2: this CTA and its x neighbour
     const uint32_t leader_cta = my_cta & ~1u;
     const int kb_total = (p.K + BK - 1) / BK;
     const int kb0 = (int) ((long long) kb_total * rank / S), kb1 = (int) ((long long) kb_total * (rank + 1) / S);
@@ -347,7 +366,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
         for (int s = 0; s < kStages; s++) {
             mbar_init(smem_u32(&bar_full[s]), CG);                  // leader's arrive.expect_tx (+ the peer's remote arrive)
-            mbar_init(smem_u32(&bar_empty[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), NX);                 // NX = 2: both CTAs' MMA commits
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(smem_u32(&bar_acc_full[b]), 1);
@@ -365,7 +384,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         }
     }
     tcgen05_fence_before();
-    if (CG == 2) cg::this_cluster().sync();                 // the peer arrives on the leader's barriers: they must exist first
+    if (CX == 2) cg::this_cluster().sync();                 // the peer arrives on / multicasts into this CTA: its barriers must exist first
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -400,6 +419,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         for (int h = 0; h < kBRows / kBBox; h++) {
                             tma_load_2d_pair(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
                             tma_load_2d_pair(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
+                        }
+                    } else if (NX == 2) {
+                        // own half of the A rows to both CTAs (the maps have 64-row boxes); the other half arrives from the peer
+                        mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
+                        const uint32_t half = (uint32_t) x_rank * (BM / 2) * BK * 4;
+                        tma_load_2d_mc(base + half, &tm_a_hi, full, kc, m0 + x_rank * (BM / 2), mc_mask);
+                        tma_load_2d_mc(base + BM * BK * 4 + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask);
+#pragma unroll
+                        for (int h = 0; h < kBRows / kBBox; h++) {
+                            tma_load_2d(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full, kc, b_row0 + h * kBBox);
+                            tma_load_2d(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full, kc, b_row0 + h * kBBox);
                         }
                     } else {
                         mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
@@ -453,6 +483,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                             first = false;
                         }
                         if (CG == 2) umma_commit_pair(smem_u32(&bar_empty[s]), pair_mask);   // frees the slot in both CTAs
+                        else if (NX == 2) umma_commit_mc(smem_u32(&bar_empty[s]), mc_mask);
                         else umma_commit(smem_u32(&bar_empty[s]));
                     }
                     if (CG == 2) umma_commit_pair(smem_u32(&bar_acc_full[buf]), pair_mask);   // chunk complete, both CTAs' epilogues
@@ -460,12 +491,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 }
             }
         }
-        role_sync<(S > 1)>();
+        role_sync<(S > 1 || NX == 2)>();                    // NX = 2: the peer may still multicast into this CTA's stages
         // BN = 128: these warps are idle by now and keep their registers: they take a share of the epilogue.
         // BN = 256: they gave their registers to the epilogue warps (setmaxnreg) and only keep the rendezvous.
         if (BN < 256 && !(p.dry & 8))
-            cooperative_epilogue<BN, S, CG, Cfg::kThreads>(p, data, rank, pair_rank, m0, n0, (int) threadIdx.x);
-        role_sync<(S > 1 || CG == 2)>();
+            cooperative_epilogue<BN, S, CG, Cfg::kThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
+        role_sync<(S > 1 || CX == 2)>();
     } else {
         // ===== epilogue warps: promote TMEM chunks into fp32 registers (round-to-nearest adds) =====
         if (BN >= 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
@@ -506,9 +537,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             for (int j = 0; j < kColsPerWarp; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
-        role_sync<(S > 1)>();                                                      // every partial tile (of the split) is parked
-        if (!(p.dry & 8)) cooperative_epilogue<BN, S, CG, kEpiThreads>(p, data, rank, pair_rank, m0, n0, (int) threadIdx.x);
-        role_sync<(S > 1 || CG == 2)>();                                           // nobody leaves while peers still read / share TMEM
+        role_sync<(S > 1 || NX == 2)>();                                           // every partial tile (of the split) is parked
+        if (!(p.dry & 8)) cooperative_epilogue<BN, S, CG, kEpiThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
+        role_sync<(S > 1 || CX == 2)>();                                           // nobody leaves while peers still read / share TMEM
     }
 
     if (warp == kEpiWarps + 1) {
@@ -729,6 +760,7 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 struct GemmOp {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap b_hi64, b_lo64;          // the same B with 64-row boxes (256 x 128 CTA-pair tiles)
+    CUtensorMap a_hi64, a_lo64;          // the same A with 64-row boxes (operand multicast between two N tiles)
     GemmParams p;
     char name[48];
 };
@@ -882,6 +914,7 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         memset(&op, 0, sizeof(op));
         const int K = plan->nodes[l], N = plan->nodes[l + 1];
         bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, plan->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, plan->ld[l], BM) &&
+                  make_map(&op.a_hi64, t->x_hi[l], cap, K, plan->ld[l], BM / 2) && make_map(&op.a_lo64, t->x_lo[l], cap, K, plan->ld[l], BM / 2) &&
                   make_map(&op.b_hi, plan->w_hi[l], N, K, plan->ld[l], 128) && make_map(&op.b_lo, plan->w_lo[l], N, K, plan->ld[l], 128) &&
                   make_map(&op.b_hi64, plan->w_hi[l], N, K, plan->ld[l], 64) && make_map(&op.b_lo64, plan->w_lo[l], N, K, plan->ld[l], 64);
         if (!ok) return cudaErrorInvalidValue;
@@ -897,6 +930,7 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         memset(&op, 0, sizeof(op));
         const int K = plan->nodes[l + 1], N = plan->nodes[l];
         bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM) &&
+                  make_map(&op.a_hi64, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM / 2) && make_map(&op.a_lo64, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM / 2) &&
                   make_map(&op.b_hi, plan->wt_hi[l], N, K, plan->ld[l + 1], 128) && make_map(&op.b_lo, plan->wt_lo[l], N, K, plan->ld[l + 1], 128) &&
                   make_map(&op.b_hi64, plan->wt_hi[l], N, K, plan->ld[l + 1], 64) && make_map(&op.b_lo64, plan->wt_lo[l], N, K, plan->ld[l + 1], 64);
         if (!ok) return cudaErrorInvalidValue;
@@ -937,28 +971,34 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     }
     cfg.attrs = attr;
     cfg.numAttrs = n;
+    if (cluster_z > 0 && getenv("ANNF_CLUSTER_DEBUG")) {     // diagnostics: how many clusters of this shape the device co-schedules
+        int max_clusters = -1;
+        cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
+        fprintf(stderr, "[annf] grid (%u,%u,%u) cluster (%d,1,%d) smem %zu: %d clusters of %u needed, %d co-resident\n", grid.x, grid.y, grid.z,
+                cluster_x, cluster_z, smem, (int) (grid.x * grid.y * grid.z) / (cluster_x * cluster_z), (unsigned) (cluster_x * cluster_z), max_clusters);
+    }
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int BN, int S, int CG>
+template <int BN, int S, int CG, int NX = 1>
 static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CG>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (err != cudaSuccess) return err;
-        if (CG * S > 8) {
-            err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (CG * NX * S > 8) {
+            err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG, NX>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (err != cudaSuccess) return err;
         }
         configured[dev] = true;
     }
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM * CG - 1) / (BM * CG);
     constexpr bool kBox64 = Cfg::kBRows < 128;
-    return launch_pdl(gemm3x_kernel<BN, S, CG>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG, S,
-                      op.a_hi, op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo, p);
+    return launch_pdl(gemm3x_kernel<BN, S, CG, NX>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG * NX, S,
+                      NX == 2 ? op.a_hi64 : op.a_hi, NX == 2 ? op.a_lo64 : op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo, p);
 }
 
 static int pick_split(int tiles, int k_blocks, int sm_count) {
@@ -993,6 +1033,24 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         if (p.N >= 256 && s2 == 1 && pair_ctas >= t->sm_count / 2) mode = 512;
         else mode = (tiles128 > t->sm_count && pick_split(tiles128, kb, t->sm_count) == 1) ? 256 : 128;
     }
+    if (mode == 132 && ((p.N + 127) / 128) % 2 == 0) {
+        // 128 x 128 tiles, two N neighbours per cluster sharing the A tile by TMA multicast; split-K <= 4 keeps 2 x S portable
+        const int tiles = ((p.N + 127) / 128) * ((R + BM - 1) / BM);
+        // B200 co-schedules 33 clusters of 4, 24 of 6 but only 15 of 8 CTAs at 1 CTA / SM (cudaOccupancyMaxActiveClusters,
+        // ANNF_CLUSTER_DEBUG=1): a grid of 16 eight-CTA clusters runs in two waves.  So: the largest split whose 2 x S
+        // clusters are all co-resident.
+        int s = std::min(4, pick_split(tiles, kb, t->sm_count));
+        if (t->force_split > 0 && kb <= 32) s = std::min(4, t->force_split);
+        if (s == 4 && tiles / 2 > 15) s = 3;
+        if (const char* env = getenv("ANNF_GEMM_NX_SPLIT")) s = atoi(env);
+        switch (s) {
+        case 4: return launch_gemm_t<128, 4, 1, 2>(op, p, stream);
+        case 3: return launch_gemm_t<128, 3, 1, 2>(op, p, stream);
+        case 2: return launch_gemm_t<128, 2, 1, 2>(op, p, stream);
+        default: return launch_gemm_t<128, 1, 1, 2>(op, p, stream);
+        }
+    }
+    if (mode == 132) mode = 128;
     if (mode == 130) {
         // 256 x 128 tiles on CTA pairs: each CTA stages its own 128 rows of A and 64 of the 128 rows of B (48 KB per K-block
         // instead of 64), split along K inside the same cluster (2 x S CTAs, S <= 4 keeps the cluster portable)

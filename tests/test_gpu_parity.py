@@ -279,10 +279,11 @@ def test_tensor_core_path_matches_oracle(nodes, types, R):
     np.testing.assert_array_equal(f, f2)
 
 
-@pytest.mark.parametrize("bn", ["128", "256", "512", "130"])
+@pytest.mark.parametrize("bn", ["128", "256", "512", "130", "132"])
 def test_tensor_core_tile_widths_agree(bn, monkeypatch):
     """Every GEMM tile shape against the oracle — 128 wide (4 epilogue warps), 256 wide (8 epilogue warps + setmaxnreg)
-    and "512" = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, multicast commits) — with split-K 4 and 8,
+    "512" = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, multicast commits), "130" = 256 x 128 CTA-pair tiles and
+    "132" = 128-wide tiles whose N-neighbours share the A tile by TMA multicast — with split-K 3, 4 and 8,
     ragged N (600 = 2*256 + 88), ragged K and an odd number of 128-row M tiles."""
     monkeypatch.setenv("ANNF_GEMM_BN", bn)
     nodes, types, R = [1200, 600, 320, 6], ["Tanh", "Tanh", "Tanh"], 150
