@@ -539,3 +539,40 @@ def test_low_latency_single_kernel_lane_groupings(lg, monkeypatch):
         e_ref, f_ref = port.evaluate(force, seen)
         assert abs(e - e_ref) <= 1e-11 * abs(e_ref)
         assert np.abs(frc - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+
+
+@pytest.mark.parametrize("config", ["c3", "c4"])
+def test_baseline_batched_shapes_at_full_size(config):
+    """BASELINE configs 3 (256 windows of 21-40-4 Circular) and 4 (1024 walkers of 180-100-100-3) at their full replica
+    counts on the fp64 tensor (DMMA) path: parity on a sample of replicas spread over the CTAs, then the size-independent
+    properties — zero net force (centroid removal), exact doubling with the force constant, replica independence
+    (a permutation of the batch permutes the results bit for bit), determinism."""
+    cfg = synthetic.CONFIGS[config]
+    force = synthetic.make_config(config)
+    R, atoms = cfg["replicas"], cfg["atoms"]
+    pos = synthetic.make_positions(atoms, R, seed=2024)
+    cen = synthetic.make_centers(force, R, seed=2025)
+    e, f, kernel = run_batched(force, pos, cen, precision="auto")
+    assert kernel.info()["batched_path"] == "dmma" and kernel.info()["precision_batched"] == "fp64"
+    sample = np.unique(np.concatenate([np.arange(0, R, 37), [R - 1]]))
+    e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
+    np.testing.assert_allclose(e[sample], e_ref, rtol=1e-11)
+    assert max_norm_rel(f[sample], f_ref) <= 1e-6                          # forces leave the device as fp32
+    assert np.abs(f.sum(axis=1)).max() <= 1e-5 * np.abs(f).max()           # zero net force per replica
+    e_again, f_again, _ = run_batched(force, pos, cen, precision="auto")
+    np.testing.assert_array_equal(e_again, e)
+    np.testing.assert_array_equal(f_again, f)
+    perm = np.random.default_rng(1).permutation(R)
+    e_p, f_p, _ = run_batched(force, pos[perm], cen[perm], precision="auto")
+    if config == "c4":
+        # every CTA walks the weight stream from its own starting chunk, so the summation order (not the sum) depends on
+        # which CTA a replica lands in: equal to a few ulps of fp64, forces equal after rounding to fp32 almost always
+        np.testing.assert_allclose(e_p, e[perm], rtol=1e-13)
+        assert max_norm_rel(f_p, f[perm].astype(np.float64)) <= 1e-6
+    else:
+        np.testing.assert_array_equal(e_p, e[perm])
+        np.testing.assert_array_equal(f_p, f[perm])
+    force.set_force_constant(2.0 * force.get_force_constant())
+    e2, f2, _ = run_batched(force, pos, cen, precision="auto")
+    np.testing.assert_allclose(e2, 2.0 * e, rtol=1e-14)
+    assert max_norm_rel(f2, 2.0 * f.astype(np.float64)) <= 2e-7
