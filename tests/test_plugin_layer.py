@@ -49,3 +49,34 @@ def test_plugin_layer_runs_the_reference_style_tests():
     out = subprocess.run([os.path.join(CPP, "_build", "test_ann_plugin")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.strip().endswith("Done"), out.stdout
+
+
+def test_serialization_proxy_round_trip():
+    """ANN_Force <-> SerializationNode, bit-exact, registered at library load (CPU only)."""
+    exe = os.path.join(CPP, "_build", "test_serialization")
+    subprocess.run(["make", "-C", CPP, exe], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "serialization ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cmake_packaging_builds_the_plugin_libraries(tmp_path):
+    """The CMake project of the plugin (same targets and install layout as the reference's: libANN in lib/, libANN_CUDA in
+    lib/plugins) configures, builds against the OpenMM stand-in, passes its ctest, installs, and the CUDA plugin exports
+    the entry points OpenMM's plugin loader and static users call (CudaANN_KernelFactory.cpp:43-65 of the reference)."""
+    import shutil
+    if shutil.which("cmake") is None or not os.path.exists(os.path.join(ROOT, "ann_force_b200", "libannforce_b200.so")):
+        pytest.skip("needs cmake and the built kernel library")
+    build, prefix = str(tmp_path / "build"), str(tmp_path / "prefix")
+    run = lambda *cmd, **kw: subprocess.run(cmd, check=True, capture_output=True, text=True, **kw)
+    run("cmake", "-S", PLUGIN, "-B", build, "-DANN_USE_OPENMM_STUB=ON", "-DCMAKE_INSTALL_PREFIX=" + prefix)
+    run("cmake", "--build", build, "-j4")
+    assert "100% tests passed" in run("ctest", cwd=build).stdout
+    run("cmake", "--install", build)
+    assert os.path.exists(os.path.join(prefix, "lib", "libANN.so"))
+    assert os.path.exists(os.path.join(prefix, "lib", "plugins", "libANN_CUDA.so"))
+    assert os.path.exists(os.path.join(prefix, "include", "openmm", "ANN_Force.h"))
+    symbols = run("nm", "-D", "--defined-only", os.path.join(prefix, "lib", "plugins", "libANN_CUDA.so")).stdout
+    for name in ("registerPlatforms", "registerKernelFactories", "registerANN_CudaKernelFactories"):
+        assert re.search(r"\bT %s\b" % name, symbols), name
+    api = run("nm", "-D", "--defined-only", os.path.join(prefix, "lib", "libANN.so")).stdout
+    assert re.search(r"\bT registerANNSerializationProxies\b", api)
