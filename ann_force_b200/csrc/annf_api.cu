@@ -673,8 +673,15 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
     return ANNF_OK;
 }
 
+#ifndef ANNF_PHASE_CLOCKS
+#define ANNF_NEED_PHASE_CLOCKS(name) return fail(ANNF_ERR_UNSUPPORTED, name ": this build carries no phase clocks (make EXTRA=-DANNF_PHASE_CLOCKS)")
+#else
+#define ANNF_NEED_PHASE_CLOCKS(name) do { } while (0)
+#endif
+
 annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16) {
     if (!h || !clocks16) return fail(ANNF_ERR_INVALID, "annf_debug_single_phases: NULL argument");
+    ANNF_NEED_PHASE_CLOCKS("annf_debug_single_phases");
     DeviceGuard guard(h->device);
     ANNF_CUDA(cudaDeviceSynchronize());
     ANNF_CUDA(read_single_phase_clocks(reinterpret_cast<long long*>(clocks16)));
@@ -683,6 +690,7 @@ annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16) {
 
 annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks32) {
     if (!h || !clocks32) return fail(ANNF_ERR_INVALID, "annf_debug_stream_phases: NULL argument");
+    ANNF_NEED_PHASE_CLOCKS("annf_debug_stream_phases");
     DeviceGuard guard(h->device);
     ANNF_CUDA(cudaDeviceSynchronize());
     if (h->dmma) ANNF_CUDA(read_dmma_phase_clocks(reinterpret_cast<long long*>(clocks32)));

@@ -55,7 +55,11 @@ struct DmmaArgs {
 
 // Diagnostic: clock64() of thread 0 / CTA 0 at the phase boundaries of the last launch (annf_debug_stream_phases).
 __device__ long long g_dmma_phase_clock[64];
+#ifdef ANNF_PHASE_CLOCKS        // diagnostic build only (make EXTRA=-DANNF_PHASE_CLOCKS): the product kernels carry no instrumentation
 #define ANNF_DPHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_dmma_phase_clock[i] = clock64(); } while (0)
+#else
+#define ANNF_DPHASE(i) do { } while (0)
+#endif
 
 namespace {
 

@@ -32,7 +32,11 @@ namespace annf {
 
 // Diagnostic: clock64() of thread 0 / CTA 0 at the phase boundaries of the last launch (annf_debug_single_phases).
 __device__ long long g_single_phase_clock[16];
+#ifdef ANNF_PHASE_CLOCKS        // diagnostic build only (make EXTRA=-DANNF_PHASE_CLOCKS): the product kernels carry no instrumentation
 #define ANNF_PHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_single_phase_clock[i] = clock64(); } while (0)
+#else
+#define ANNF_PHASE(i) do { } while (0)
+#endif
 
 constexpr int kSingleThreads = 256;
 constexpr int kSingleWarps = kSingleThreads / 32;

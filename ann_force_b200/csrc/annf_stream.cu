@@ -55,8 +55,12 @@ struct StreamArgs {
 
 // Diagnostic: clock64() of thread 0 / CTA 0 at the phase boundaries of the last launch (annf_debug_stream_phases):
 // [0] start, [1] barriers + prologue loads, [2] features, [3 + p] pass p done, [3 + npass] head, [4 + npass] end.
-__device__ long long g_stream_phase_clock[64];     // [32 + p]: cycles warp 0 waited for weights in pass p; [48 + p]: epilogue of pass p
+__device__ long long g_stream_phase_clock[64];
+#ifdef ANNF_PHASE_CLOCKS        // diagnostic build only (make EXTRA=-DANNF_PHASE_CLOCKS): the product kernels carry no instrumentation
 #define ANNF_SPHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_stream_phase_clock[i] = clock64(); } while (0)
+#else
+#define ANNF_SPHASE(i) do { } while (0)
+#endif
 
 namespace {
 
@@ -144,12 +148,9 @@ __device__ __forceinline__ void stream_pass(const StreamPlan& plan, int p, int& 
 
     // every CTA walks the chunks of a pass from its own starting point (see the producer)
     int tt = blockIdx.x % nch;
-    long long waited = 0;
     for (int t = 0; t < nch; t++, chunk++) {
         const int s = chunk & (kStreamStages - 1);
-        const long long w0 = clock64();
         bar_wait(full0 + 8 * s, (chunk / kStreamStages) & 1);
-        waited += clock64() - w0;
         if (busy) {
             const T* wc = reinterpret_cast<const T*>(ring + (size_t) s * kStreamStageBytes) + jbase;
             const int row0 = tt * rows_per, nrows = min(rows_per, n_loop - row0);
@@ -161,8 +162,6 @@ __device__ __forceinline__ void stream_pass(const StreamPlan& plan, int p, int& 
         if (lane == 0) bar_arrive(empty0 + 8 * s);
         if (++tt == nch) tt = 0;
     }
-    const long long e0 = clock64();
-    if (threadIdx.x == 0 && blockIdx.x == 0) g_stream_phase_clock[32 + p] = waited;
 
     if (ks > 1) {
         // partial sums meet in shared memory: scratch[part][r][node], node stride padded so that the epilogue's
@@ -198,7 +197,6 @@ __device__ __forceinline__ void stream_pass(const StreamPlan& plan, int p, int& 
         }
     }
     compute_sync();
-    if (threadIdx.x == 0 && blockIdx.x == 0) g_stream_phase_clock[48 + p] = clock64() - e0;
 }
 
 }  // namespace

@@ -153,13 +153,14 @@ ANNF_API annf_status annf_eval_batched_host(annf_handle h, int32_t num_replicas,
                                    int32_t atoms_per_replica, const float* centers_host, float* forces_host,
                                    double* energies_host);
 
-/* Diagnostic: SM clock (clock64) of thread 0 at the phase boundaries of the most recent annf_eval_openmm launch:
+/* Diagnostics, available in builds made with -DANNF_PHASE_CLOCKS only (otherwise ANNF_ERR_UNSUPPORTED; the product kernels carry
+ * no instrumentation).  SM clock (clock64) of thread 0 at the phase boundaries of the most recent annf_eval_openmm launch:
  * [0] start, [1] features, [2] weights staged, [3] forward, [4] energy head, [5] backward, [6] forces issued.  Synchronises. */
 ANNF_API annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16);
 
-/* Diagnostic: the same for CTA 0 of the most recent streamed batched launch (annf_eval_batched, batched_path 2):
- * [0] start, [1] prologue loads, [2] features, [3 + p] contraction p done (forward then backward), then head and end;
- * [32 + p] cycles warp 0 waited for weights in contraction p, [48 + p] its epilogue.  64 values.  Synchronises. */
+/* Diagnostic: the same for CTA 0 of the most recent streamed batched launch (annf_eval_batched, batched_path 2 or 3):
+ * [0] start, [1] prologue loads, [2] features, [3 + p] contraction p done (forward then backward), then head and end.
+ * 64 values.  Synchronises. */
 ANNF_API annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks64);
 
 /* Per-kernel device timing with CUDA events on the launching stream (for the roofline line). */

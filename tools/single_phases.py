@@ -1,4 +1,5 @@
-"""Per-phase SM-cycle breakdown of the single-replica kernel (diagnostic)."""
+"""(Needs a diagnostic build of the library: make -C ann_force_b200/csrc clean && make -C ann_force_b200/csrc EXTRA=-DANNF_PHASE_CLOCKS)
+Per-phase SM-cycle breakdown of the single-replica kernel (diagnostic)."""
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
