@@ -521,8 +521,14 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
 
 // out[r] = sum_c M[r][c] * v[c] for r < nrows (M rows contiguous in shared memory); 2^lg lanes of one warp share a row and
 // the lane with g == 0 receives the sum in epi(r, sum).  Called by every thread of the CTA.
-// The terms of a lane are taken 16 at a time with every load issued before the first FMA: the loop is latency-bound, and
-// a strided loop with run-time bounds costs ~90 cycles per 4 terms.
+// The terms of a lane are taken 8 at a time with every load issued before the first FMA: the loop is latency-bound, and
+// a strided loop with run-time bounds costs ~90 cycles per 4 terms.  (16 at a time measured 4 % slower end to end: this
+// code runs a handful of times per launch, so its size counts as much as its schedule.)
+#ifndef ANNF_MATVEC_BLOCK
+#define ANNF_MATVEC_BLOCK 8
+#endif
+constexpr int kMatvecBlock = ANNF_MATVEC_BLOCK;           // terms of a lane in flight together
+
 template <typename Epi>
 __device__ __forceinline__ void fast_matvec(const double* M, int ncols, int nrows, const double* v, int lg, Epi epi) {
     const int tid = threadIdx.x;
@@ -533,17 +539,17 @@ __device__ __forceinline__ void fast_matvec(const double* M, int ncols, int nrow
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         if (valid) {
             const double* row = M + (size_t) r * ncols;
-            for (int c0 = g; c0 < ncols; c0 += 16 * G) {
-                double w[16], x[16];
+            for (int c0 = g; c0 < ncols; c0 += kMatvecBlock * G) {
+                double w[kMatvecBlock], x[kMatvecBlock];
 #pragma unroll
-                for (int u = 0; u < 16; u++) {
+                for (int u = 0; u < kMatvecBlock; u++) {
                     const int c = c0 + u * G;
                     const bool in = c < ncols;
                     w[u] = in ? row[c] : 0.0;
                     x[u] = in ? v[c] : 0.0;
                 }
 #pragma unroll
-                for (int u = 0; u < 16; u += 4) {
+                for (int u = 0; u < kMatvecBlock; u += 4) {
                     acc0 = fma(w[u], x[u], acc0);
                     acc1 = fma(w[u + 1], x[u + 1], acc1);
                     acc2 = fma(w[u + 2], x[u + 2], acc2);
@@ -770,9 +776,9 @@ static int pick_lanes_log2(int nrows, int ncols) {
         const int G = 1 << lg;
         if (lg > 0 && G > ncols) break;
         const int terms = (ncols + G - 1) / G;
-        const int blocks = (terms + 15) / 16;
+        const int blocks = (terms + kMatvecBlock - 1) / kMatvecBlock;
         const int passes = (nrows * G + kSingleThreads - 1) / kSingleThreads;
-        const double cost = (passes > 0 ? passes : 1) * (blocks * (40.0 + 6.5 * (terms < 16 ? terms : 16)) + 65.0 * lg);
+        const double cost = (passes > 0 ? passes : 1) * (blocks * (40.0 + 6.5 * (terms < kMatvecBlock ? terms : kMatvecBlock)) + 65.0 * lg);
         if (cost < best_cost) { best_cost = cost; best = lg; }
     }
     if (forced >= 0 && forced <= 5 && (1 << forced) <= (ncols > 1 ? ncols : 1)) best = forced;

@@ -406,6 +406,8 @@ def main():
                     ours_us_per_step_stream=ours["gpu_us_per_step"], ours_us_per_step_graph=ours["graph_us_per_step"],
                     speedup_stream=leg["us_per_step_stream"] / ours["gpu_us_per_step"],
                     speedup_graph=leg["us_per_step_graph"] / ours["graph_us_per_step"],
+                    empty_kernel_us_per_step_stream=leg.get("empty_kernel_us_per_step_stream"),
+                    empty_kernel_us_per_step_graph=leg.get("empty_kernel_us_per_step_graph"),
                     note="both are bound by kernel launch + a chain of dependent layers; ours runs fp64, the legacy scheme fp32")
         except Exception as exc:       # noqa: BLE001
             e2e["legacy_error"] = str(exc)[:200]

@@ -102,6 +102,9 @@ __global__ void legacy_style_kernel(LegacyArgs a) {
     }
 }
 
+// launch floor: what one dependent kernel launch per MD step costs when the kernel does nothing
+__global__ void empty_kernel(int* sink) { if (sink != nullptr && threadIdx.x == 1024) *sink = 0; }
+
 static double lcg(unsigned long long& s) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return ((s >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0; }
 
 template <typename T> static T* upload(const std::vector<T>& v) {
@@ -161,9 +164,33 @@ int main(int argc, char** argv) {
     cudaStreamSynchronize(stream);
     float ms_graph = 0.f;
     cudaEventElapsedTime(&ms_graph, e0, e1);
+    // the same two measurements for an empty kernel
+    for (int i = 0; i < 200; i++) empty_kernel<<<1, 128, 0, stream>>>(nullptr);
+    cudaStreamSynchronize(stream);
+    cudaEventRecord(e0, stream);
+    for (int i = 0; i < steps; i++) empty_kernel<<<1, 128, 0, stream>>>(nullptr);
+    cudaEventRecord(e1, stream);
+    cudaStreamSynchronize(stream);
+    float ms_empty = 0.f;
+    cudaEventElapsedTime(&ms_empty, e0, e1);
+    cudaGraph_t graph2; cudaGraphExec_t exec2;
+    cudaStreamBeginCapture(stream, cudaStreamCaptureModeGlobal);
+    for (int i = 0; i < 100; i++) empty_kernel<<<1, 128, 0, stream>>>(nullptr);
+    cudaStreamEndCapture(stream, &graph2);
+    cudaGraphInstantiate(&exec2, graph2, 0);
+    cudaGraphLaunch(exec2, stream);
+    cudaStreamSynchronize(stream);
+    cudaEventRecord(e0, stream);
+    for (int i = 0; i < steps / 100; i++) cudaGraphLaunch(exec2, stream);
+    cudaEventRecord(e1, stream);
+    cudaStreamSynchronize(stream);
+    float ms_empty_graph = 0.f;
+    cudaEventElapsedTime(&ms_empty_graph, e0, e1);
     const cudaError_t err = cudaGetLastError();
     printf("{\"what\": \"restatement of the legacy plugin's generated kernel (NOT the legacy plugin)\", \"network\": \"21-40-2 Tanh/Tanh, 7 of 22 atoms, fp32\", "
-           "\"steps\": %d, \"us_per_step_stream\": %.4f, \"us_per_step_graph\": %.4f, \"cuda_error\": \"%s\"}\n",
-           steps, 1e3 * ms / steps, 1e3 * ms_graph / (steps / 100 * 100), cudaGetErrorString(err));
+           "\"steps\": %d, \"us_per_step_stream\": %.4f, \"us_per_step_graph\": %.4f, \"empty_kernel_us_per_step_stream\": %.4f, "
+           "\"empty_kernel_us_per_step_graph\": %.4f, \"cuda_error\": \"%s\"}\n",
+           steps, 1e3 * ms / steps, 1e3 * ms_graph / (steps / 100 * 100), 1e3 * ms_empty / steps, 1e3 * ms_empty_graph / (steps / 100 * 100),
+           cudaGetErrorString(err));
     return err == cudaSuccess ? 0 : 1;
 }
