@@ -576,3 +576,44 @@ def test_baseline_batched_shapes_at_full_size(config):
     e2, f2, _ = run_batched(force, pos, cen, precision="auto")
     np.testing.assert_allclose(e2, 2.0 * e, rtol=1e-14)
     assert max_norm_rel(f2, 2.0 * f.astype(np.float64)) <= 2e-7
+
+
+def _random_cartesian_net(rng, hidden_types=("Tanh", "Linear"), out_types=("Tanh", "Linear", "Circular", "Softmax")):
+    """A random Cartesian network: 2-5 node layers, ragged widths (not multiples of 4, 8 or 32), a selection scattered in
+    a larger system."""
+    depth = int(rng.integers(2, 6))
+    n_sel = int(rng.integers(2, 40))
+    n_atoms = n_sel + int(rng.integers(0, 25))
+    nodes = [3 * n_sel] + [int(rng.integers(3, 150)) for _ in range(depth - 2)]
+    out_type = str(rng.choice(out_types))
+    n_out = int(rng.integers(1, 7))
+    if out_type == "Circular":
+        n_out = 2 * max(1, n_out // 2)
+    nodes.append(n_out)
+    types = [str(rng.choice(hidden_types)) for _ in range(depth - 2)] + [out_type]
+    atom_index = (np.sort(rng.permutation(n_atoms)[:n_sel]) + 1).tolist()
+    force = synthetic.make_force(nodes, types, n_sel, seed=int(rng.integers(1 << 30)), atom_index=atom_index)
+    return force, nodes, types, n_atoms
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_networks_single_and_batched(seed):
+    """Randomised shapes through the default kernels (low-latency single-replica kernel incl. its cluster form, DMMA and
+    generic batched kernels) against the oracle at the fp64 bars.  Softmax outputs are kept away from saturation by the
+    synthetic weights; Circular outputs exercise the +-6.2832 wrap."""
+    rng = np.random.default_rng(1000 + seed)
+    force, nodes, types, n_atoms = _random_cartesian_net(rng)
+    R = int(rng.integers(1, 70))
+    pos = synthetic.make_positions(n_atoms, R, seed=seed)
+    cen = synthetic.make_centers(force, R, seed=seed + 1)
+    e, f, kernel = run_batched(force, pos, cen, precision="fp64")
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=1e-10, err_msg=str((nodes, types, kernel.info()["batched_path"])))
+    assert max_norm_rel(f, f_ref) <= 1e-6, (nodes, types, kernel.info()["batched_path"])
+    # the same network, one replica on OpenMM-layout buffers with its own centre
+    f0, _, _, _ = force, None, None, None
+    f0.set_potential_center([float(c) for c in cen[0].astype(np.float64)])
+    e1, f1, seen, k1 = run_single(f0, pos[0].astype(np.float64), "double")
+    e1_ref, f1_ref = port.evaluate(f0, seen)
+    assert abs(e1 - e1_ref) <= 1e-10 * abs(e1_ref), (nodes, types, k1.info()["single_path"])
+    assert np.abs(f1 - f1_ref).max() <= 1e-9 * np.abs(f1_ref).max() + 2 * FIXED_POINT_ULP, (nodes, types, k1.info()["single_path"])
