@@ -10,8 +10,12 @@ is BASELINE.json configs[4] sharded the way it is quoted: 4500-512-512-8 encoder
 1024 replicas PER GPU (8192 on 8 GPUs) — weak scaling, no collective on the force path.  Other
 BASELINE shapes are selectable with --workload (c2 single replica on OpenMM buffers, c3, c4).
 
-Prints ONE JSON line (rank 0).  `value` is whole-job evaluations/s with inputs resident in HBM;
-`e2e` is the same metric through the host-buffer C-ABI entry (H2D + eval + D2H every step).
+Prints ONE JSON line (rank 0).  `value` is whole-job evaluations/s with inputs resident in HBM (the timed steps are
+replayed from a CUDA graph over rotating buffer sets larger than L2; device time, max over ranks); `e2e` is the same metric
+through the host-buffer C-ABI entry (H2D + eval + D2H every step) — for the single-replica workload, through the C++ plugin
+layer on device-resident OpenMM buffers; `roofline` comes from a second, event-instrumented pass (never graph-replayed);
+`cpu_baseline` is the reference's own CPU kernel on the host cores.  The default 1-GPU line also carries short runs of the
+other BASELINE shapes (`other_workloads`: c2 with the legacy-restatement comparison, c3, c4).
 """
 from __future__ import annotations
 
