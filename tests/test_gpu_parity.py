@@ -617,3 +617,27 @@ def test_random_networks_single_and_batched(seed):
     e1_ref, f1_ref = port.evaluate(f0, seen)
     assert abs(e1 - e1_ref) <= 1e-10 * abs(e1_ref), (nodes, types, k1.info()["single_path"])
     assert np.abs(f1 - f1_ref).max() <= 1e-9 * np.abs(f1_ref).max() + 2 * FIXED_POINT_ULP, (nodes, types, k1.info()["single_path"])
+
+
+@pytest.mark.parametrize("config", ["c3", "c4"])
+def test_batched_finite_differences(config):
+    """The reference's own integration check (test_ANN_package.cpp:175-180) on the batched fp64 path: analytic forces
+    against central differences of the batched energies.  Coordinates sit on a 2^-14 grid and the step is 2^-10, so the
+    displaced fp32 inputs are exact."""
+    cfg = synthetic.CONFIGS[config]
+    force = synthetic.make_config(config)
+    atoms, R = cfg["atoms"], 3
+    pos = np.round(synthetic.make_positions(atoms, R, seed=11).astype(np.float64) * 2 ** 14) / 2 ** 14
+    cen = synthetic.make_centers(force, R, seed=12)
+    _, analytic, _ = run_batched(force, pos, cen, precision="fp64")
+    h = 2.0 ** -10
+    rng = np.random.default_rng(0)
+    for atom, comp in zip(rng.integers(0, atoms, 6), rng.integers(0, 3, 6)):
+        plus, minus = pos.copy(), pos.copy()
+        plus[:, atom, comp] += h
+        minus[:, atom, comp] -= h
+        e_p, _, _ = run_batched(force, plus, cen, precision="fp64")
+        e_m, _, _ = run_batched(force, minus, cen, precision="fp64")
+        numeric = -(e_p - e_m) / (2 * h)
+        scale = np.abs(analytic).max(axis=(1, 2))
+        assert np.all(np.abs(numeric - analytic[:, atom, comp]) <= 2e-3 * scale), (atom, comp, numeric, analytic[:, atom, comp])
