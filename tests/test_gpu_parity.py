@@ -641,3 +641,18 @@ def test_batched_finite_differences(config):
         numeric = -(e_p - e_m) / (2 * h)
         scale = np.abs(analytic).max(axis=(1, 2))
         assert np.all(np.abs(numeric - analytic[:, atom, comp]) <= 2e-3 * scale), (atom, comp, numeric, analytic[:, atom, comp])
+
+
+@pytest.mark.parametrize("nodes", [[300, 512, 512, 8], [96, 1024, 6], [30, 700, 700, 2]])
+def test_forced_fp64_on_wide_networks_picks_a_kernel_that_fits(nodes):
+    """fp64 forced on networks near and beyond the shared-memory limits of the streamed kernels: whichever batched
+    kernel the handle falls back to (DMMA -> FMA stream -> generic), the result meets the fp64 bars."""
+    atoms = nodes[0] // 3
+    types = ["Tanh"] * (len(nodes) - 1)
+    force = synthetic.make_force(nodes, types, atoms, seed=61)
+    R = 19
+    pos = synthetic.make_positions(atoms, R, seed=62)
+    e, f, kernel = run_batched(force, pos, None, precision="fp64")
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
+    np.testing.assert_allclose(e, e_ref, rtol=1e-10, err_msg=kernel.info()["batched_path"])
+    assert max_norm_rel(f, f_ref) <= 1e-6, kernel.info()["batched_path"]
