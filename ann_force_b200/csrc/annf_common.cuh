@@ -144,7 +144,7 @@ __device__ inline double output_head(int type, int n, const double* z, int zs, c
     } else {
         for (int j = 0; j < n; j++) {
             const double zz = z[j * zs];
-            const double a = (type == ANNF_TANH) ? tanh(zz) : zz;
+            const double a = (type == ANNF_TANH) ? annf_tanh(zz) : zz;
             const double d = (a - center[j]) * k;                      // :266-269
             e += 0.5 * k * (a - center[j]) * (a - center[j]);          // .h:93-96
             dz[j * ds] = (type == ANNF_TANH) ? d * (1 - a * a) : d;    // :343-354

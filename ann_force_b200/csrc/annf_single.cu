@@ -98,7 +98,7 @@ __device__ void activate_layer(int type, int n, const double* z, double* a) {
     if (type == ANNF_LINEAR) {
         for (int j = tid; j < n; j += blockDim.x) a[j] = z[j];
     } else if (type == ANNF_TANH) {
-        for (int j = tid; j < n; j += blockDim.x) a[j] = tanh(z[j]);
+        for (int j = tid; j < n; j += blockDim.x) a[j] = annf_tanh(z[j]);
     } else if (type == ANNF_CIRCULAR) {
         for (int j = tid; j < n / 2; j += blockDim.x) {
             const double p = z[2 * j], q = z[2 * j + 1], r = sqrt(p * p + q * q);
