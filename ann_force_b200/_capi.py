@@ -10,8 +10,8 @@ LIB_PATH = os.path.join(HERE, "libannforce_b200.so")
 
 LINEAR, TANH, CIRCULAR, SOFTMAX = 0, 1, 2, 3
 LAYER_CODES = {"Linear": LINEAR, "Tanh": TANH, "Circular": CIRCULAR, "Softmax": SOFTMAX}
-PREC_AUTO, PREC_FP64, PREC_FP32, PREC_TF32X3 = 0, 1, 2, 3
-PRECISIONS = {"auto": PREC_AUTO, "fp64": PREC_FP64, "fp32": PREC_FP32, "tf32x3": PREC_TF32X3}
+PREC_AUTO, PREC_FP64, PREC_FP32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"auto": PREC_AUTO, "fp64": PREC_FP64, "fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "f16x3": PREC_F16X3}
 PRECISION_NAMES = {v: k for k, v in PRECISIONS.items()}
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, 1, 2, 3, 4
 FLAG_POSQ_DOUBLE, FLAG_ENERGY_DOUBLE, FLAG_SKIP_FORCES, FLAG_SKIP_ENERGY = 1, 2, 4, 8
@@ -52,6 +52,7 @@ SYMBOLS = {
     "annf_destroy": (C.c_int, [C.c_void_p]),
     "annf_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "annf_update_parameters": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_double, C.c_void_p]),
+    "annf_reserve": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "annf_set_atom_order": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "annf_eval_openmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
     "annf_eval_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

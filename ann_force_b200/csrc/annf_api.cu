@@ -50,8 +50,10 @@ cudaError_t launch_dmma(const NetView& net, const StreamPlan& plan, const void* 
 cudaError_t read_dmma_phase_clocks(long long* out64);
 // annf_tensor.cu
 struct TensorPlan;
-TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, std::string* why_not);
+TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, const std::vector<double>& bias64,
+                               int kind, std::string* why_not);     // kind: 0 = TF32 pairs, 1 = scaled fp16 pairs
 void tensor_plan_destroy(TensorPlan* plan);
+cudaError_t tensor_plan_reserve(TensorPlan* plan, const NetView& net, int R, cudaStream_t stream);
 cudaError_t tensor_plan_run(TensorPlan* plan, Profiler* prof, const NetView& net, int R,
                             const float* coords, int atoms_per_replica, const float* centers, float* forces,
                             double* energies, cudaStream_t stream, long long* launches, int slot_index);
@@ -135,7 +137,12 @@ struct annf_context {
     double *W64 = nullptr, *Wt64 = nullptr, *b64 = nullptr, *center = nullptr, *k_dev = nullptr, *staged = nullptr;
     float *W32 = nullptr, *Wt32 = nullptr, *b32 = nullptr;
     int *sel_atoms = nullptr, *sel_slots = nullptr, *inverse = nullptr, *pairs_local = nullptr, *dihedrals_local = nullptr;
-    double* staged_host = nullptr;   // pinned, [num_center + 1]
+    // annf_update_parameters stages through a ring of pinned slots + device slots, each guarded by an event, so the call
+    // is stream-ordered and returns without waiting (it only waits if kParamSlots updates are still in flight)
+    static constexpr int kParamSlots = 4;
+    double* staged_host = nullptr;   // pinned, [kParamSlots][num_center + 1]
+    cudaEvent_t param_ev[kParamSlots] = {};
+    int param_next = 0;
     TensorPlan* tensor = nullptr;
     int tensor_slot = 0;             // which activation-buffer set of the tensor plan the next batched call uses
     Profiler prof;
@@ -169,6 +176,8 @@ void release(annf_context* h) {
     cudaFree(h->sel_atoms); cudaFree(h->sel_slots); cudaFree(h->inverse); cudaFree(h->pairs_local); cudaFree(h->dihedrals_local);
     cudaFree(h->h_coords); cudaFree(h->h_centers); cudaFree(h->h_forces); cudaFree(h->h_energies);
     if (h->staged_host) cudaFreeHost(h->staged_host);
+    for (int i = 0; i < annf_context::kParamSlots; i++)
+        if (h->param_ev[i]) cudaEventDestroy(h->param_ev[i]);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     if (h->host_stream2) cudaStreamDestroy(h->host_stream2);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
@@ -228,11 +237,19 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
         if (desc->num_backbone_atoms <= 0 || 3 * desc->num_backbone_atoms != desc->num_of_nodes[0])
             return fail(ANNF_ERR_INVALID, "Cartesian input: 3 * %d selected atoms != %d input nodes",
                         desc->num_backbone_atoms, desc->num_of_nodes[0]);                          // CudaANN_Kernels.cpp:188
+        std::vector<char> seen((size_t) desc->num_system_atoms + 1, 0);
         for (int i = 0; i < desc->num_backbone_atoms; i++) {
             const int a = desc->index_of_backbone_atoms[i];
             if (a < 1 || a > desc->num_system_atoms)
                 return fail(ANNF_ERR_INVALID, "index_of_backbone_atoms[%d] = %d is outside 1..%d (indices are 1-based)", i, a,
                             desc->num_system_atoms);
+            // The reference accumulates forces per list entry (ANN_ReferenceKernels.cpp:401), so a repeated atom would need
+            // its contributions summed; the batched kernels write one force row per selected atom.  A repeated atom in a
+            // backbone list is a user error in every known use, so it is rejected here rather than evaluated two ways.
+            if (seen[a])
+                return fail(ANNF_ERR_INVALID, "index_of_backbone_atoms lists atom %d more than once (entry %d); each selected atom must "
+                            "appear once", a, i);
+            seen[a] = 1;
         }
     } else if (desc->data_type_in_input_layer == ANNF_INPUT_DIHEDRAL_COS_SIN) {
         if (desc->num_dihedrals <= 0 || !desc->dihedrals || 2 * desc->num_dihedrals != desc->num_of_nodes[0])
@@ -249,7 +266,7 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     } else {
         return fail(ANNF_ERR_INVALID, "data_type_in_input_layer = %d", desc->data_type_in_input_layer);
     }
-    if (desc->precision < ANNF_PREC_AUTO || desc->precision > ANNF_PREC_TF32X3)
+    if (desc->precision < ANNF_PREC_AUTO || desc->precision > ANNF_PREC_F16X3)
         return fail(ANNF_ERR_INVALID, "precision = %d", desc->precision);
 
     int count = 0;
@@ -344,8 +361,9 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     ANNF_CUDA_H(upload(&h->pairs_local, pairs_local));
     ANNF_CUDA_H(upload(&h->dihedrals_local, dihedrals_local));
     ANNF_CUDA_H(cudaMalloc((void**) &h->inverse, sizeof(int) * h->num_system_atoms));
-    ANNF_CUDA_H(cudaMalloc((void**) &h->staged, sizeof(double) * (desc->num_center + 1)));
-    ANNF_CUDA_H(cudaMallocHost((void**) &h->staged_host, sizeof(double) * (desc->num_center + 1)));
+    ANNF_CUDA_H(cudaMalloc((void**) &h->staged, sizeof(double) * annf_context::kParamSlots * (desc->num_center + 1)));
+    ANNF_CUDA_H(cudaMallocHost((void**) &h->staged_host, sizeof(double) * annf_context::kParamSlots * (desc->num_center + 1)));
+    for (int i = 0; i < annf_context::kParamSlots; i++) ANNF_CUDA_H(cudaEventCreateWithFlags(&h->param_ev[i], cudaEventDisableTiming));
     net.W64 = h->W64; net.Wt64 = h->Wt64; net.b64 = h->b64;
     net.W32 = h->W32; net.Wt32 = h->Wt32; net.b32 = h->b32;
     net.center = h->center; net.k_dev = h->k_dev; net.num_center = desc->num_center;
@@ -397,25 +415,27 @@ annf_status annf_create(const annf_desc* desc, annf_handle* out) {
     h->tile_fp32 = net.nodes[L - 1] <= 256 ? pick_tile(false) : 0;
     int prec = desc->precision;
     std::string why_not;
-    if (prec == ANNF_PREC_AUTO || prec == ANNF_PREC_TF32X3) {
-        h->tensor = tensor_plan_create(net, coeff_rows, &why_not);
-        if (h->tensor == nullptr && prec == ANNF_PREC_TF32X3) {
+    // AUTO takes the fp16-pair tensor path for wide networks: same 11 + 11-bit operand split as 3xTF32, half the operand
+    // bytes and twice the MMA rate; ANNF_AUTO_TENSOR=tf32x3 switches AUTO back for comparisons.
+    int auto_tensor = ANNF_PREC_F16X3;
+    if (const char* env = getenv("ANNF_AUTO_TENSOR"))
+        if (strcmp(env, "tf32x3") == 0) auto_tensor = ANNF_PREC_TF32X3;
+    const bool small_net = h->macs <= (1 << 16) && h->tile_fp64 > 0;
+    if (prec == ANNF_PREC_TF32X3 || prec == ANNF_PREC_F16X3 || (prec == ANNF_PREC_AUTO && !small_net)) {
+        const int want = prec == ANNF_PREC_AUTO ? auto_tensor : prec;
+        h->tensor = tensor_plan_create(net, coeff_rows, b64, want == ANNF_PREC_F16X3 ? 1 : 0, &why_not);
+        if (h->tensor == nullptr && prec != ANNF_PREC_AUTO) {
             release(h);
-            return fail(ANNF_ERR_UNSUPPORTED, "TF32X3 tensor-core path unavailable for this network: %s", why_not.c_str());
+            return fail(ANNF_ERR_UNSUPPORTED, "%s tensor-core path unavailable for this network: %s",
+                        prec == ANNF_PREC_F16X3 ? "F16X3" : "TF32X3", why_not.c_str());
         }
+        if (h->tensor != nullptr) prec = want;
     }
-    if (prec == ANNF_PREC_AUTO) {
-        if (h->macs <= (1 << 16) && h->tile_fp64 > 0) prec = ANNF_PREC_FP64;
-        else if (h->tensor != nullptr) prec = ANNF_PREC_TF32X3;
-        else prec = ANNF_PREC_FP32;
-    }
-    if (prec != ANNF_PREC_TF32X3 && h->tensor != nullptr) {
-        tensor_plan_destroy(h->tensor);
-        h->tensor = nullptr;
-    }
+    if (prec == ANNF_PREC_AUTO) prec = small_net ? ANNF_PREC_FP64 : ANNF_PREC_FP32;
+    const bool tensor_path = prec == ANNF_PREC_TF32X3 || prec == ANNF_PREC_F16X3;
     h->prec_batched = prec;
-    h->batched_path = prec == ANNF_PREC_TF32X3 ? 1 : 0;
-    if (prec != ANNF_PREC_TF32X3) {
+    h->batched_path = tensor_path ? 1 : 0;
+    if (!tensor_path) {
         std::vector<double> s64;
         std::vector<float> s32;
         std::vector<unsigned char> statics;
@@ -487,13 +507,27 @@ annf_status annf_update_parameters(annf_handle h, const double* potential_center
                     num_center, h->net.num_center);
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
-    memcpy(h->staged_host, potential_center, sizeof(double) * num_center);
-    h->staged_host[num_center] = force_constant;
-    ANNF_CUDA(cudaMemcpyAsync(h->staged, h->staged_host, sizeof(double) * (num_center + 1), cudaMemcpyHostToDevice, s));
-    set_parameters_kernel<<<(num_center + 1 + 127) / 128, 128, 0, s>>>(h->center, h->staged, num_center, h->k_dev);
+    const int slot = h->param_next;
+    h->param_next = (slot + 1) % annf_context::kParamSlots;
+    ANNF_CUDA(cudaEventSynchronize(h->param_ev[slot]));          // the update that last used this slot has left the host buffer
+    double* host = h->staged_host + (size_t) slot * (num_center + 1);
+    double* dev = h->staged + (size_t) slot * (num_center + 1);
+    memcpy(host, potential_center, sizeof(double) * num_center);
+    host[num_center] = force_constant;
+    ANNF_CUDA(cudaMemcpyAsync(dev, host, sizeof(double) * (num_center + 1), cudaMemcpyHostToDevice, s));
+    set_parameters_kernel<<<(num_center + 1 + 127) / 128, 128, 0, s>>>(h->center, dev, num_center, h->k_dev);
     ANNF_CUDA(cudaGetLastError());
-    ANNF_CUDA(cudaStreamSynchronize(s));
+    ANNF_CUDA(cudaEventRecord(h->param_ev[slot], s));
     h->launches++;
+    return ANNF_OK;
+}
+
+annf_status annf_reserve(annf_handle h, int32_t max_replicas, void* stream) {
+    if (!h) return fail(ANNF_ERR_INVALID, "annf_reserve: NULL handle");
+    if (max_replicas < 0) return fail(ANNF_ERR_INVALID, "annf_reserve: max_replicas = %d", max_replicas);
+    DeviceGuard guard(h->device);
+    if (h->tensor != nullptr && max_replicas > 0)
+        ANNF_CUDA(tensor_plan_reserve(h->tensor, h->net, max_replicas, (cudaStream_t) stream));
     return ANNF_OK;
 }
 

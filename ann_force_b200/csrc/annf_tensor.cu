@@ -29,6 +29,7 @@
 // all peers through DSMEM in a fixed order (deterministic), then runs the epilogue on it.
 #include <cooperative_groups.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -46,10 +47,25 @@ namespace cg = cooperative_groups;
 namespace annf {
 
 constexpr int BM = 128;               // replicas per tile = UMMA M
-constexpr int BK = 32;                // fp32 elements per K-block = 128 bytes = one swizzle span
-constexpr int UMMA_K = 8;             // tf32: 32 bytes per instruction along K
+constexpr int kBlockBytes = 128;      // bytes of one operand row in a K-block = one swizzle span
+constexpr int kStepBytes = 32;        // bytes along K consumed by one MMA instruction (8 tf32 or 16 f16 values)
+constexpr int kStepsPerBlock = kBlockBytes / kStepBytes;
 
-constexpr int kChunk = 2;             // K-blocks accumulated in TMEM between promotions (K = 64: 24 chained MMAs)
+// Operand kind of the contraction.  Both split an fp32 value v into a pair hi + lo with 11 significant bits each, and a
+// product costs three MMAs (lo*hi, hi*lo, hi*hi); they differ in the container:
+//   KIND_TF32  hi, lo are fp32 words rounded to TF32 (cvt.rna); tcgen05 kind::tf32, 8 values per 32-byte K-step
+//   KIND_F16   hi, lo are IEEE halves of v * 2^e, e a per-row power of two that puts the row's largest magnitude just below
+//              2^15 (fp16 has TF32's 10-bit mantissa but a 5-bit exponent: the scale buys the range back); tcgen05 kind::f16,
+//              16 values per K-step: HALF the operand bytes through L2 / shared memory and TWICE the MMA rate of kind::tf32.
+//              The epilogue multiplies the fp32 accumulator by 2^-(e_row + e_col), an exact operation.
+enum { KIND_TF32 = 0, KIND_F16 = 1 };
+template <int KIND> struct KindOf;
+template <> struct KindOf<KIND_TF32> { typedef float elem; static constexpr int kBlockElems = 32; };
+template <> struct KindOf<KIND_F16> { typedef __half elem; static constexpr int kBlockElems = 64; };
+constexpr int kExpTarget = 14;        // KIND_F16: a row is scaled so that its magnitude bound lies in [2^13, 2^14]
+constexpr int kExpClamp = 60;         // |e| <= 60, so 2^-(e_row + e_col) is always a normal fp32 number
+
+constexpr int kChunkDefault = 2;      // K-blocks accumulated in TMEM between promotions (24 chained MMAs); ANNF_TENSOR_CHUNK overrides
 
 enum { EPI_STORE = 0, EPI_BIAS_TANH = 1, EPI_BIAS_LINEAR = 2, EPI_TANH_GRAD = 3, EPI_LINEAR_GRAD = 4, EPI_FORCE = 5 };
 
@@ -57,13 +73,19 @@ struct GemmParams {
     int M, N, K;
     int epi;
     const float* bias;                // [N]               (EPI_BIAS_*)
-    const float* aux_hi;              // [M][ld_aux] activations of the layer being differentiated (EPI_TANH_GRAD)
-    const float* aux_lo;
+    const void* aux_hi;               // [M][ld_aux] activations of the layer being differentiated (EPI_TANH_GRAD); elem of the kind
+    const void* aux_lo;
     int ld_aux;
-    float* out_hi;                    // [M][ld_out]  (EPI_STORE: the plain fp32 result; EPI_FORCE: forces [M][atoms][3])
-    float* out_lo;
+    void* out_hi;                     // [M][ld_out] elem of the kind (EPI_STORE: the plain fp32 result; EPI_FORCE: fp32 forces [M][atoms][3])
+    void* out_lo;
     int ld_out;                       //              (EPI_FORCE: 3 * atoms_per_replica)
+    // KIND_F16 only: binary exponents of the power-of-two scales.  Stored operand = value * 2^exp.
+    const int* a_exp;                 // [M] rows of A (activations / gradients going in)
+    const int* b_exp;                 // [N] rows of B (weights)
+    const int* out_exp;               // [M] rows of the result (activations / gradients coming out); unused by EPI_FORCE / EPI_STORE
+    const int* aux_exp;               // [M] rows of aux
     const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
+    int chunk;                        // K-blocks accumulated in TMEM between two promotions into the fp32 register accumulators
     int dry;                          // experiments (ANNF_TENSOR_DRY=1): return immediately, to measure the launch floor
 };
 
@@ -100,14 +122,24 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, N = BN, K = 8 (tf32), issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, N = BN, K = 32 bytes (8 tf32 or 16 f16 values), issued by ONE thread
+template <int KIND>
+__device__ __forceinline__ void umma_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -130,10 +162,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     return (uint64_t) ((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
-}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a / b format at bits 7 / 10, both K-major, N>>3 at bit 17, M>>4 at bit 24
 
 __device__ __forceinline__ float tf32_round(float v) {
     uint32_t r;
@@ -151,7 +180,7 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kEpiWarps = BN / 32;                                   // each owns 32 TMEM lanes x 128 columns
     static constexpr int kThreads = (kEpiWarps + 4) * 32;                       // + producer warp, MMA warp, 2 idle (warpgroup padding)
     static constexpr int kBRows = BN / CG;                                      // rows of B this CTA stages
-    static constexpr int kStageBytes = (2 * BM + 2 * kBRows) * BK * 4;
+    static constexpr int kStageBytes = (2 * BM + 2 * kBRows) * kBlockBytes;
     static constexpr int kStages = kStageBytes > 80 * 1024 ? 2 : (kStageBytes > 48 * 1024 ? 3 : 4);
     static constexpr int kStagingLd = BN + 4;                                   // fp32 elements, padded against bank conflicts
     static constexpr int kStagingBytes = BM * kStagingLd * 4;
@@ -179,13 +208,23 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+template <int KIND>
+__device__ __forceinline__ void umma_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 // arrive (once the MMAs issued so far retire) on the barrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
@@ -204,30 +243,68 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
 }
-__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (m >> 4) << 24);
+// a / b format field: kind::tf32 -> 2 (TF32); kind::f16 -> 0 (F16)
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int kind, int m, int n) {
+    return (1u << 4) | ((kind == KIND_TF32 ? 2u : 0u) << 7) | ((kind == KIND_TF32 ? 2u : 0u) << 10) | ((uint32_t) (n >> 3) << 17) |
+           ((uint32_t) (m >> 4) << 24);
 }
 
 // One epilogue element group = 4 consecutive columns of one output row, in two steps so that callers can issue the global
 // loads of several groups before any of the dependent math (the epilogue loop is otherwise bound by one L2 round trip per group).
-struct EpiAux { float4 a, b; };
+struct EpiAux { float4 a, b, unscale; float out_scale; };
 
+__device__ __forceinline__ float exp2i(int k) { return __int_as_float((k + 127) << 23); }   // 2^k exactly, -126 <= k <= 127
+
+__device__ __forceinline__ float4 half4_to_float4(uint2 raw) {
+    const __half2 p0 = *reinterpret_cast<const __half2*>(&raw.x), p1 = *reinterpret_cast<const __half2*>(&raw.y);
+    const float2 f0 = __half22float2(p0), f1 = __half22float2(p1);
+    return make_float4(f0.x, f0.y, f1.x, f1.y);
+}
+
+// v (already multiplied by the row's power-of-two scale) -> hi = rn_f16(v), lo = rn_f16(v - hi), four values packed
+__device__ __forceinline__ void split_f16x4(float4 v, uint2& hi, uint2& lo) {
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+template <int KIND>
 __device__ __forceinline__ EpiAux epilogue_load(const GemmParams& p, int m, int n) {
     EpiAux x;
     x.a = make_float4(0.f, 0.f, 0.f, 0.f);
     x.b = x.a;
+    x.unscale = make_float4(1.f, 1.f, 1.f, 1.f);
+    x.out_scale = 1.f;
+    if (KIND == KIND_F16) {
+        const int ea = __ldg(p.a_exp + m);
+        const int4 eb = __ldg(reinterpret_cast<const int4*>(p.b_exp + n));
+        x.unscale = make_float4(exp2i(-(ea + eb.x)), exp2i(-(ea + eb.y)), exp2i(-(ea + eb.z)), exp2i(-(ea + eb.w)));
+        if (p.epi != EPI_STORE && p.epi != EPI_FORCE) x.out_scale = exp2i(__ldg(p.out_exp + m));
+    }
     if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
         x.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     } else if (p.epi == EPI_TANH_GRAD) {
-        x.a = __ldg(reinterpret_cast<const float4*>(p.aux_hi + (size_t) m * p.ld_aux + n));
-        x.b = __ldg(reinterpret_cast<const float4*>(p.aux_lo + (size_t) m * p.ld_aux + n));
+        if (KIND == KIND_F16) {
+            // a = (hi + lo) * 2^-e: the sum of the pair is exact in fp32 and so is the power-of-two unscale
+            const float un = exp2i(-__ldg(p.aux_exp + m));
+            const float4 h = half4_to_float4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.aux_hi) + (size_t) m * p.ld_aux + n)));
+            const float4 l = half4_to_float4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.aux_lo) + (size_t) m * p.ld_aux + n)));
+            x.a = make_float4((h.x + l.x) * un, (h.y + l.y) * un, (h.z + l.z) * un, (h.w + l.w) * un);
+        } else {
+            x.a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.aux_hi) + (size_t) m * p.ld_aux + n));
+            x.b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.aux_lo) + (size_t) m * p.ld_aux + n));
+        }
     }
     return x;
 }
 
+template <int KIND>
 __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int n, float4 v, const EpiAux& x) {
+    if (KIND == KIND_F16) { v.x *= x.unscale.x; v.y *= x.unscale.y; v.z *= x.unscale.z; v.w *= x.unscale.w; }
     if (p.epi == EPI_STORE) {
-        *reinterpret_cast<float4*>(p.out_hi + (size_t) m * p.ld_out + n) = v;
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out + n) = v;
         return;
     }
     if (p.epi == EPI_FORCE) {
@@ -235,7 +312,7 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
         // first connection with the Jacobian of "divide by s, subtract the centroid" folded in at plan creation
         // (ANN_ReferenceKernels.cpp:137-145, :397-410), so the accumulator already IS the force.
         const float4 f = v;
-        float* row = p.out_hi + (size_t) m * p.ld_out;
+        float* row = static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out;
         if (p.sel_atoms == nullptr) {
             *reinterpret_cast<float4*>(row + n) = f;
         } else {
@@ -255,16 +332,23 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
         const float a0 = x.a.x + x.b.x, a1 = x.a.y + x.b.y, a2 = x.a.z + x.b.z, a3 = x.a.w + x.b.w;
         v.x *= (1.f - a0 * a0); v.y *= (1.f - a1 * a1); v.z *= (1.f - a2 * a2); v.w *= (1.f - a3 * a3);
     }
+    if (KIND == KIND_F16) {
+        uint2 hi, lo;
+        split_f16x4(make_float4(v.x * x.out_scale, v.y * x.out_scale, v.z * x.out_scale, v.w * x.out_scale), hi, lo);
+        *reinterpret_cast<uint2*>(static_cast<__half*>(p.out_hi) + (size_t) m * p.ld_out + n) = hi;
+        *reinterpret_cast<uint2*>(static_cast<__half*>(p.out_lo) + (size_t) m * p.ld_out + n) = lo;
+        return;
+    }
     float4 hi, lo;
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-    *reinterpret_cast<float4*>(p.out_hi + (size_t) m * p.ld_out + n) = hi;
-    *reinterpret_cast<float4*>(p.out_lo + (size_t) m * p.ld_out + n) = lo;
+    *reinterpret_cast<float4*>(static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out + n) = hi;
+    *reinterpret_cast<float4*>(static_cast<float*>(p.out_lo) + (size_t) m * p.ld_out + n) = lo;
 }
 
 // Cooperative epilogue over the parked tile(s): thread t of kGroupThreads walks (row, 4-column) groups with consecutive lanes
 // along a row — 512-byte coalesced global accesses — summing the S split-K partials (own + peers', through DSMEM) in a fixed
 // order, with the auxiliary global loads of four groups issued ahead of the dependent math.
-template <int BN, int S, int CG, int kGroupThreads, int CX = CG>
+template <int KIND, int BN, int S, int CG, int kGroupThreads, int CX = CG>
 __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int kRows = (BM + S - 1) / S;                                        // rows this CTA finishes (S = 3: 43, 43, 42)
@@ -294,7 +378,7 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsign
             ok[u] = (g0 + u) < kGroups && v < kRows * kVecPerRow && row < BM && mm[u] < p.M && nn[u] < p.N;
             sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok[u]) {
-                aux[u] = epilogue_load(p, mm[u], nn[u]);
+                aux[u] = epilogue_load<KIND>(p, mm[u], nn[u]);
 #pragma unroll
                 for (int r = 0; r < S; r++) {                                      // fixed order: deterministic
                     const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
@@ -304,7 +388,7 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsign
         }
 #pragma unroll
         for (int u = 0; u < kBatch; u++)
-            if (ok[u]) epilogue_finish(p, mm[u], nn[u], sum[u], aux[u]);
+            if (ok[u]) epilogue_finish<KIND>(p, mm[u], nn[u], sum[u], aux[u]);
     }
 }
 
@@ -321,11 +405,12 @@ template <bool kCluster> __device__ __forceinline__ void role_sync() {
 // NX = 2 (1-CTA tiles only): the two CTAs at x = 2i, 2i + 1 of a cluster compute neighbouring N tiles of the SAME rows, so
 // they need the same A tile: each loads half of its rows and TMA-multicasts them into both CTAs (48 instead of 64 KB of
 // L2 -> SM traffic per K-block and CTA).  A stage is free again when BOTH CTAs' MMAs have retired (multicast commit).
-template <int BN, int S, int CG, int NX = 1>
+template <int KIND, int BN, int S, int CG, int NX = 1>
 __global__ void __launch_bounds__(GemmCfg<BN, CG>::kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmParams p) {
     using Cfg = GemmCfg<BN, CG>;
+    constexpr int BK = KindOf<KIND>::kBlockElems;           // operand values per K-block (one 128-byte swizzle span)
     constexpr int kStages = Cfg::kStages;
     constexpr int kEpiWarps = Cfg::kEpiWarps;
     constexpr int kColsPerWarp = 128;                       // accumulator columns held in registers by one epilogue thread
@@ -358,6 +443,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const int kb_total = (p.K + BK - 1) / BK;
     const int kb0 = (int) ((long long) kb_total * rank / S), kb1 = (int) ((long long) kb_total * (rank + 1) / S);
     const int num_kb = kb1 - kb0;
+    const int kChunk = p.chunk;
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
 
     pdl_launch_dependents();                                // the next kernel may start its own prologue now
@@ -414,31 +500,31 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         if (pair_rank == 0) mbar_expect_tx(full, (uint32_t) (2 * Cfg::kStageBytes));   // both CTAs' bytes land here
                         else mbar_arrive_cluster(full_leader);
                         tma_load_2d_pair(base, &tm_a_hi, full_leader, kc, m0);
-                        tma_load_2d_pair(base + BM * BK * 4, &tm_a_lo, full_leader, kc, m0);
+                        tma_load_2d_pair(base + BM * kBlockBytes, &tm_a_lo, full_leader, kc, m0);
 #pragma unroll
                         for (int h = 0; h < kBRows / kBBox; h++) {
-                            tma_load_2d_pair(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
-                            tma_load_2d_pair(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
+                            tma_load_2d_pair(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
+                            tma_load_2d_pair(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
                         }
                     } else if (NX == 2) {
                         // own half of the A rows to both CTAs (the maps have 64-row boxes); the other half arrives from the peer
                         mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
-                        const uint32_t half = (uint32_t) x_rank * (BM / 2) * BK * 4;
+                        const uint32_t half = (uint32_t) x_rank * (BM / 2) * kBlockBytes;
                         tma_load_2d_mc(base + half, &tm_a_hi, full, kc, m0 + x_rank * (BM / 2), mc_mask);
-                        tma_load_2d_mc(base + BM * BK * 4 + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask);
+                        tma_load_2d_mc(base + BM * kBlockBytes + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask);
 #pragma unroll
                         for (int h = 0; h < kBRows / kBBox; h++) {
-                            tma_load_2d(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full, kc, b_row0 + h * kBBox);
-                            tma_load_2d(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full, kc, b_row0 + h * kBBox);
+                            tma_load_2d(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox);
+                            tma_load_2d(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox);
                         }
                     } else {
                         mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
                         tma_load_2d(base, &tm_a_hi, full, kc, m0);
-                        tma_load_2d(base + BM * BK * 4, &tm_a_lo, full, kc, m0);
+                        tma_load_2d(base + BM * kBlockBytes, &tm_a_lo, full, kc, m0);
 #pragma unroll
                         for (int h = 0; h < kBRows / kBBox; h++) {                // TMA boxes are at most 256 rows; use 128-row boxes
-                            tma_load_2d(base + 2 * BM * BK * 4 + h * kBBox * BK * 4, &tm_b_hi, full, kc, b_row0 + h * kBBox);
-                            tma_load_2d(base + 2 * BM * BK * 4 + kBRows * BK * 4 + h * kBBox * BK * 4, &tm_b_lo, full, kc, b_row0 + h * kBBox);
+                            tma_load_2d(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox);
+                            tma_load_2d(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox);
                         }
                     }
                 }
@@ -446,7 +532,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         } else if (warp == kEpiWarps + 1 && pair_rank == 0) {
             // ----- MMA issuer (one thread of the leader CTA).  Chunk c accumulates into TMEM buffer c & 1. -----
             if (lane == 0) {
-                constexpr uint32_t idesc = umma_idesc_tf32_mn(BM * CG, BN);
+                constexpr uint32_t idesc = umma_idesc_mn(KIND, BM * CG, BN);
                 const uint16_t pair_mask = (uint16_t) (3u << leader_cta);          // both CTAs of this pair
                 int i = 0;
                 for (int c = 0; c < num_chunks; c++) {
@@ -463,22 +549,22 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed (both CTAs)
                         tcgen05_fence_after();
                         const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
-                        const uint32_t a_hi = base, a_lo = base + BM * BK * 4;
-                        const uint32_t b_hi = base + 2 * BM * BK * 4, b_lo = b_hi + kBRows * BK * 4;
+                        const uint32_t a_hi = base, a_lo = base + BM * kBlockBytes;
+                        const uint32_t b_hi = base + 2 * BM * kBlockBytes, b_lo = b_hi + kBRows * kBlockBytes;
 #pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                        for (int kk = 0; kk < kStepsPerBlock; kk++) {
                             if (p.dry & 2) break;                                  // experiments: no tensor-core work
-                            const uint32_t off = kk * UMMA_K * 4;                  // 32 bytes along K inside the swizzle span
+                            const uint32_t off = kk * kStepBytes;                   // 32 bytes along K inside the swizzle span
                             const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
                             const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
                             if (CG == 2) {
-                                umma_tf32_pair(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);   // small terms first
-                                umma_tf32_pair(tmem_acc, dah, dbl, idesc, 1u);
-                                umma_tf32_pair(tmem_acc, dah, dbh, idesc, 1u);
+                                umma_mma_pair<KIND>(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);   // small terms first
+                                umma_mma_pair<KIND>(tmem_acc, dah, dbl, idesc, 1u);
+                                umma_mma_pair<KIND>(tmem_acc, dah, dbh, idesc, 1u);
                             } else {
-                                umma_tf32(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);
-                                umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
-                                umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                                umma_mma<KIND>(tmem_acc, dal, dbh, idesc, first ? 0u : 1u);
+                                umma_mma<KIND>(tmem_acc, dah, dbl, idesc, 1u);
+                                umma_mma<KIND>(tmem_acc, dah, dbh, idesc, 1u);
                             }
                             first = false;
                         }
@@ -495,7 +581,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         // BN = 128: these warps are idle by now and keep their registers: they take a share of the epilogue.
         // BN = 256: they gave their registers to the epilogue warps (setmaxnreg) and only keep the rendezvous.
         if (BN < 256 && !(p.dry & 8))
-            cooperative_epilogue<BN, S, CG, Cfg::kThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
+            cooperative_epilogue<KIND, BN, S, CG, Cfg::kThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
         role_sync<(S > 1 || CX == 2)>();
     } else {
         // ===== epilogue warps: promote TMEM chunks into fp32 registers (round-to-nearest adds) =====
@@ -538,7 +624,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
         role_sync<(S > 1 || NX == 2)>();                                           // every partial tile (of the split) is parked
-        if (!(p.dry & 8)) cooperative_epilogue<BN, S, CG, kEpiThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
+        if (!(p.dry & 8)) cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
         role_sync<(S > 1 || CX == 2)>();                                           // nobody leaves while peers still read / share TMEM
     }
 
@@ -552,10 +638,31 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // SIMT companions
 // ------------------------------------------------------------------------------------------------
-// prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), centroid in fp64, write the TF32 pair.
+// KIND_F16 bookkeeping: how the per-row scale exponents are derived without a second pass over the data.  The exponent of
+// the input row comes from its exact largest magnitude; every later tensor gets an exponent from a BOUND on its magnitudes,
+// propagated through the layers with the weights' L1 norms (fp16 keeps 2^-24 .. 2^15: a bound that is 2^10 too generous
+// still leaves every significant value with its full 11 + 11 bits).
+struct ExpChain {
+    float fwd_gain[kMaxLayers];     // max_n sum_k |W_l[n][k]|       (connection l, forward)
+    float fwd_bias[kMaxLayers];     // max_n |b_l[n]|
+    float bwd_gain[kMaxLayers];     // max_i sum_j |W_l[j][i]|       (connection l, backward)
+    int* x_exp[kMaxLayers];         // [R] per forward tensor X_l, l = 0..L-2   (written by prep)
+    int* d_exp[kMaxLayers];         // [R] per gradient tensor D_l, l = 1..L-2  (written by head)
+};
+
+__device__ __forceinline__ int exp_for_bound(float bound) {
+    if (!(bound > 0.f) || !(bound < 3.0e38f)) return 0;
+    int q;
+    frexpf(bound, &q);                                      // bound = f * 2^q, 0.5 <= f < 1
+    return max(-kExpClamp, min(kExpClamp, kExpTarget - q));
+}
+
+// prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), centroid in fp64, write the operand pair.
 // One CTA per replica; the replica's selected coordinates are staged once in shared memory.
+template <int KIND>
 __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
-                                                  float* __restrict__ x_hi, float* __restrict__ x_lo, int ld, int contiguous) {
+                                                  void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
+                                                  ExpChain chain) {
     extern __shared__ float xs[];                           // [3 * A]
     pdl_launch_dependents();
     pdl_wait();
@@ -565,6 +672,7 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     const float* base = coords + (size_t) r * N * 3;
     __shared__ double red[8][3];
     __shared__ double com[3];
+    __shared__ float redm[8];
     double s[3] = {0.0, 0.0, 0.0};
     if (contiguous & 1) {
         // selection is atoms 0..A-1 and rows are 16-byte aligned: straight vector copy, component = index % 3
@@ -601,23 +709,76 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     __syncthreads();
     const double inv_scale = 1.0 / net.scale;
     const double c0 = com[0], c1 = com[1], c2 = com[2];
-    float* oh = x_hi + (size_t) r * ld;
-    float* ol = x_lo + (size_t) r * ld;
     // centring in fp64: a molecule far from the origin must not lose bits of (p - centroid)
+    if (KIND == KIND_TF32) {
+        float* oh = static_cast<float*>(x_hi_v) + (size_t) r * ld;
+        float* ol = static_cast<float*>(x_lo_v) + (size_t) r * ld;
+        for (int v = tid; v < n0 / 4; v += 256) {
+            const float4 p = *reinterpret_cast<const float4*>(xs + 4 * v);
+            const float e[4] = {p.x, p.y, p.z, p.w};
+            float hi[4], lo[4];
+            int c = (4 * v) % 3;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
+                split_tf32((float) (((double) e[j] - cc) * inv_scale), hi[j], lo[j]);
+                c = c == 2 ? 0 : c + 1;
+            }
+            *reinterpret_cast<float4*>(oh + 4 * v) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(ol + 4 * v) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        return;
+    }
+    // KIND_F16: the features, then the row's largest magnitude -> its scale exponent, then the scaled pair
+    float mx = 0.f;
     for (int v = tid; v < n0 / 4; v += 256) {
         const float4 p = *reinterpret_cast<const float4*>(xs + 4 * v);
         const float e[4] = {p.x, p.y, p.z, p.w};
-        float hi[4], lo[4];
+        float x[4];
         int c = (4 * v) % 3;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const double cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
-            split_tf32((float) (((double) e[j] - cc) * inv_scale), hi[j], lo[j]);
+            x[j] = (float) (((double) e[j] - cc) * inv_scale);
+            mx = fmaxf(mx, fabsf(x[j]));
             c = c == 2 ? 0 : c + 1;
         }
-        *reinterpret_cast<float4*>(oh + 4 * v) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(ol + 4 * v) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(xs + 4 * v) = make_float4(x[0], x[1], x[2], x[3]);   // same thread re-reads it below
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redm[warp] = mx;
+    __syncthreads();
+    mx = redm[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, redm[w]);
+    const int e0 = exp_for_bound(mx);
+    if (tid == 0) {
+        chain.x_exp[0][r] = e0;
+        float bound = mx;
+        for (int l = 0; l + 2 < net.L; l++) {                // X_{l+1} = act(W_l X_l + b_l)
+            bound = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + bound * chain.fwd_gain[l];
+            chain.x_exp[l + 1][r] = exp_for_bound(bound);
+        }
+    }
+    const float sc = exp2i(e0);
+    __half* oh = static_cast<__half*>(x_hi_v) + (size_t) r * ld;
+    __half* ol = static_cast<__half*>(x_lo_v) + (size_t) r * ld;
+    for (int v = tid; v < n0 / 4; v += 256) {
+        const float4 x = *reinterpret_cast<const float4*>(xs + 4 * v);
+        uint2 hi, lo;
+        split_f16x4(make_float4(x.x * sc, x.y * sc, x.z * sc, x.w * sc), hi, lo);
+        *reinterpret_cast<uint2*>(oh + 4 * v) = hi;
+        *reinterpret_cast<uint2*>(ol + 4 * v) = lo;
+    }
+}
+
+// activation m of a row stored as an operand pair: hi + lo is exact in fp32, and so is the power-of-two unscale
+template <int KIND>
+__device__ __forceinline__ float load_pair(const void* hi, const void* lo, int m, float unscale) {
+    if (KIND == KIND_F16)
+        return (__half2float(__ldg(static_cast<const __half*>(hi) + m)) + __half2float(__ldg(static_cast<const __half*>(lo) + m))) * unscale;
+    return __ldg(static_cast<const float*>(hi) + m) + __ldg(static_cast<const float*>(lo) + m);
 }
 
 // head: output layer forward (fp64 accumulate), umbrella energy + gradient (output_head), and the
@@ -629,9 +790,12 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
 // that runs once per CTA; rolled, its 128 fat CTAs delayed the cluster GEMM that follows under PDL: step 110 -> 121 us.)
 constexpr int kHeadThreads = 128;
 constexpr int kHeadMaxOut = 64;
+template <int KIND>
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, const float* __restrict__ centers,
-                                                           const float* __restrict__ a_hi, const float* __restrict__ a_lo, int ld,
-                                                           float* __restrict__ d_hi, float* __restrict__ d_lo, double* __restrict__ energies) {
+                                                           const void* __restrict__ a_hi, const void* __restrict__ a_lo, int ld,
+                                                           void* __restrict__ d_hi, void* __restrict__ d_lo, double* __restrict__ energies,
+                                                           ExpChain chain) {
+    typedef typename KindOf<KIND>::elem elem;
     pdl_launch_dependents();
     pdl_wait();
     if (R < 0) return;                                      // experiments: launch-floor dry run
@@ -644,26 +808,26 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     const double* W = net.W64 + net.w_off[L - 2];           // [nL][nH]
     const float* W32 = net.W32 + net.w_off[L - 2];
     const double* b = net.b64 + net.b_off[L - 2];
-    const float* ah = a_hi + (size_t) r * ld;
-    const float* al = a_lo + (size_t) r * ld;
+    const elem* ah = static_cast<const elem*>(a_hi) + (size_t) r * ld;
+    const elem* al = static_cast<const elem*>(a_lo) + (size_t) r * ld;
+    const float a_unscale = KIND == KIND_F16 ? exp2i(-chain.x_exp[L - 2][r]) : 1.f;
     // The loop is bound by global-load latency unless many loads are in flight: four hidden units per thread per pass, their
     // activations and 4 x 8 weights all loaded before the 32 dependent fp64 FMAs.
     for (int j0 = 0; j0 < nL; j0 += 8) {                    // 8 outputs at a time: 8 independent accumulators per thread
         double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int mb = tid; mb < nH; mb += 4 * kHeadThreads) {
-            float ahv[4], alv[4];
+            float av[4];
             double w[4][8];
 #pragma unroll
             for (int v = 0; v < 4; v++) {
                 const int m = mb + v * kHeadThreads;
-                ahv[v] = m < nH ? __ldg(ah + m) : 0.f;
-                alv[v] = m < nH ? __ldg(al + m) : 0.f;
+                av[v] = m < nH ? load_pair<KIND>(ah, al, m, a_unscale) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 8; u++) w[v][u] = (m < nH && j0 + u < nL) ? __ldg(W + (size_t) (j0 + u) * nH + m) : 0.0;
             }
 #pragma unroll
             for (int v = 0; v < 4; v++) {
-                const double a = (double) (ahv[v] + alv[v]);                     // hi + lo is exact in fp32
+                const double a = (double) av[v];
 #pragma unroll
                 for (int u = 0; u < 8; u++) acc[u] = fma(w[v][u], a, acc[u]);
             }
@@ -690,13 +854,29 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     if (tid < nL) dzf[tid] = (float) dzs[tid];
     __syncthreads();
     const int hidden_type = net.types[L - 3];
-    // the result is re-split to TF32 pairs: fp32 FMA is enough here.  Same batching: 4 hidden units per pass, loads first.
+    // KIND_F16: scale exponent of this replica's gradient rows, from a bound: |D[m]| <= max_j |dz_j| * max_m sum_j |W[j][m]|
+    float d_scale = 1.f;
+    if (KIND == KIND_F16) {
+        float mx = 0.f;
+        for (int j = 0; j < nL; j++) mx = fmaxf(mx, fabsf(dzf[j]));
+        float bound = mx * chain.bwd_gain[L - 2];
+        const int e_d = exp_for_bound(bound);
+        d_scale = exp2i(e_d);
+        if (tid == 0) {
+            chain.d_exp[L - 2][r] = e_d;
+            for (int l = L - 3; l >= 1; l--) {               // D_l = (D_{l+1} W_l) (.) act'(X_l), |act'| <= 1
+                bound *= chain.bwd_gain[l];
+                chain.d_exp[l][r] = exp_for_bound(bound);
+            }
+        }
+    }
+    // the result is re-split to operand pairs: fp32 FMA is enough here.  Same batching: 4 hidden units per pass, loads first.
     for (int mb = tid; mb < nH; mb += 4 * kHeadThreads) {
         float av[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             const int m = mb + v * kHeadThreads;
-            av[v] = m < nH ? __ldg(ah + m) + __ldg(al + m) : 0.f;
+            av[v] = m < nH ? load_pair<KIND>(ah, al, m, a_unscale) : 0.f;
         }
         for (int j = 0; j < nL; j++) {
             float w[4];
@@ -714,10 +894,17 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
             if (m >= nH) continue;
             float r = acc[v];
             if (hidden_type == ANNF_TANH) r *= (1.f - av[v] * av[v]);
-            float hi, lo;
-            split_tf32(r, hi, lo);
-            d_hi[(size_t) r_index * ld + m] = hi;
-            d_lo[(size_t) r_index * ld + m] = lo;
+            if (KIND == KIND_F16) {
+                const float rs = r * d_scale;
+                const __half hi = __float2half_rn(rs);
+                static_cast<__half*>(d_hi)[(size_t) r_index * ld + m] = hi;
+                static_cast<__half*>(d_lo)[(size_t) r_index * ld + m] = __float2half_rn(rs - __half2float(hi));
+            } else {
+                float hi, lo;
+                split_tf32(r, hi, lo);
+                static_cast<float*>(d_hi)[(size_t) r_index * ld + m] = hi;
+                static_cast<float*>(d_lo)[(size_t) r_index * ld + m] = lo;
+            }
         }
     }
 }
@@ -741,16 +928,17 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [rows][cols] fp32, row stride ld elements; box = 32 columns x box_rows rows, 128B swizzle, zero OOB fill
-static bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+// [rows][cols] fp32 or fp16, row stride ld elements; box = one 128-byte K-block x box_rows rows, 128B swizzle, zero OOB fill
+static bool make_map(CUtensorMap* map, int kind, const void* ptr, int rows, int cols, int ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    const int esz = kind == KIND_F16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t) cols, (cuuint64_t) rows};
-    cuuint64_t strides[1] = {(cuuint64_t) ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t) BK, (cuuint32_t) box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t) ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t) (kBlockBytes / esz), (cuuint32_t) box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    return fn(map, kind == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -769,31 +957,38 @@ constexpr int kPlanSlots = 2;         // independent activation-buffer sets: two
 
 struct PlanSlot {
     int cap = 0;                                    // replica capacity of the activation buffers
-    // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as TF32 pairs
-    float *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {};
+    // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as operand pairs (fp32 words or halves)
+    void *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {};
+    int *x_exp[kMaxLayers] = {}, *d_exp[kMaxLayers] = {};   // KIND_F16: per-row scale exponents of the same tensors
     std::vector<GemmOp> fwd, bwd;
 };
 
 struct TensorPlan {
     int L = 0;
+    int kind = KIND_TF32;                           // operand container of every contraction of this plan
     int nodes[kMaxLayers];
     int types[kMaxLayers];
     int ld[kMaxLayers];
     int sm_count = 148;
-    // weights (TF32 pairs), forward [n_{l+1}][ld(n_l)] and transposed [n_l][ld(n_{l+1})], l = 0..L-3
-    float *w_hi[kMaxLayers] = {}, *w_lo[kMaxLayers] = {}, *wt_hi[kMaxLayers] = {}, *wt_lo[kMaxLayers] = {}, *bias[kMaxLayers] = {};
+    // weights (operand pairs), forward [n_{l+1}][ld(n_l)] and transposed [n_l][ld(n_{l+1})], l = 0..L-3
+    void *w_hi[kMaxLayers] = {}, *w_lo[kMaxLayers] = {}, *wt_hi[kMaxLayers] = {}, *wt_lo[kMaxLayers] = {};
+    int *w_exp[kMaxLayers] = {}, *wt_exp[kMaxLayers] = {};   // KIND_F16: per-row scale exponents of the same matrices
+    ExpChain chain = {};                            // KIND_F16: norms that propagate magnitude bounds (pointers filled per slot)
     PlanSlot slots[kPlanSlots];
     bool sel_identity = false;                      // selection is atoms 0..A-1 in order
     int force_bn = 0;                               // ANNF_GEMM_BN=128|256 (1-CTA tiles) or 512 (CTA pairs) overrides the tile heuristic
     int force_split = 0;                            // ANNF_GEMM_SPLIT_SHORTK=1|2|4|8 overrides split-K for GEMMs with K <= 1024
     int dry = 0;                                    // ANNF_TENSOR_DRY=1: every kernel returns at once (launch-floor measurement)
+    int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
 };
 
 static void free_activations(PlanSlot* t) {
     for (int l = 0; l < kMaxLayers; l++) {
         cudaFree(t->x_hi[l]); cudaFree(t->x_lo[l]); cudaFree(t->d_hi[l]); cudaFree(t->d_lo[l]);
+        cudaFree(t->x_exp[l]); cudaFree(t->d_exp[l]);
         t->x_hi[l] = t->x_lo[l] = t->d_hi[l] = t->d_lo[l] = nullptr;
+        t->x_exp[l] = t->d_exp[l] = nullptr;
     }
     t->cap = 0;
 }
@@ -802,7 +997,8 @@ void tensor_plan_destroy(TensorPlan* t) {
     if (!t) return;
     for (PlanSlot& slot : t->slots) free_activations(&slot);
     for (int l = 0; l < kMaxLayers; l++) {
-        cudaFree(t->w_hi[l]); cudaFree(t->w_lo[l]); cudaFree(t->wt_hi[l]); cudaFree(t->wt_lo[l]); cudaFree(t->bias[l]);
+        cudaFree(t->w_hi[l]); cudaFree(t->w_lo[l]); cudaFree(t->wt_hi[l]); cudaFree(t->wt_lo[l]);
+        cudaFree(t->w_exp[l]); cudaFree(t->wt_exp[l]);
     }
     delete t;
 }
@@ -818,22 +1014,50 @@ static float host_tf32(float v) {          // round-to-nearest, ties away from z
     return r;
 }
 
-static cudaError_t upload_pair(const std::vector<float>& src, float** hi, float** lo) {
-    std::vector<float> h(src.size()), l(src.size());
-    for (size_t i = 0; i < src.size(); i++) {
-        h[i] = host_tf32(src[i]);
-        l[i] = host_tf32(src[i] - h[i]);
+// [rows][ld] fp32 matrix -> operand pair on the device.  KIND_F16: every row is first multiplied by 2^e, e chosen so that the
+// row's largest magnitude lies in [2^13, 2^14); the exponents are uploaded next to the pair.
+static cudaError_t upload_pair(int kind, const std::vector<float>& src, int rows, int ld, void** hi, void** lo, int** exps) {
+    cudaError_t err;
+    if (kind == KIND_TF32) {
+        std::vector<float> h(src.size()), l(src.size());
+        for (size_t i = 0; i < src.size(); i++) {
+            h[i] = host_tf32(src[i]);
+            l[i] = host_tf32(src[i] - h[i]);
+        }
+        if ((err = cudaMalloc(hi, sizeof(float) * src.size())) != cudaSuccess) return err;
+        if ((err = cudaMalloc(lo, sizeof(float) * src.size())) != cudaSuccess) return err;
+        if ((err = cudaMemcpy(*hi, h.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return err;
+        return cudaMemcpy(*lo, l.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice);
     }
-    cudaError_t err = cudaMalloc((void**) hi, sizeof(float) * src.size());
-    if (err != cudaSuccess) return err;
-    err = cudaMalloc((void**) lo, sizeof(float) * src.size());
-    if (err != cudaSuccess) return err;
-    err = cudaMemcpy(*hi, h.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice);
-    if (err != cudaSuccess) return err;
-    return cudaMemcpy(*lo, l.data(), sizeof(float) * src.size(), cudaMemcpyHostToDevice);
+    std::vector<__half> h(src.size()), l(src.size());
+    std::vector<int> e(rows, 0);
+    for (int r = 0; r < rows; r++) {
+        float mx = 0.f;
+        for (int c = 0; c < ld; c++) mx = std::max(mx, std::fabs(src[(size_t) r * ld + c]));
+        if (mx > 0.f && std::isfinite(mx)) {
+            int q;
+            std::frexp(mx, &q);
+            e[r] = std::max(-kExpClamp, std::min(kExpClamp, kExpTarget - q));
+        }
+        const float sc = std::ldexp(1.f, e[r]);
+        for (int c = 0; c < ld; c++) {
+            const float v = src[(size_t) r * ld + c] * sc;
+            const __half vh = __float2half_rn(v);
+            h[(size_t) r * ld + c] = vh;
+            l[(size_t) r * ld + c] = __float2half_rn(v - __half2float(vh));
+        }
+    }
+    if ((err = cudaMalloc(hi, sizeof(__half) * src.size())) != cudaSuccess) return err;
+    if ((err = cudaMalloc(lo, sizeof(__half) * src.size())) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**) exps, sizeof(int) * round_up(rows, 4))) != cudaSuccess) return err;
+    if ((err = cudaMemset(*exps, 0, sizeof(int) * round_up(rows, 4))) != cudaSuccess) return err;
+    if ((err = cudaMemcpy(*hi, h.data(), sizeof(__half) * src.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return err;
+    if ((err = cudaMemcpy(*lo, l.data(), sizeof(__half) * src.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return err;
+    return cudaMemcpy(*exps, e.data(), sizeof(int) * rows, cudaMemcpyHostToDevice);
 }
 
-TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, std::string* why_not) {
+TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector<double>>& coeff, const std::vector<double>& bias64,
+                               int kind, std::string* why_not) {
     auto no = [&](const char* msg) { if (why_not) *why_not = msg; return (TensorPlan*) nullptr; };
     const int L = net.L;
     if (net.input_type != ANNF_INPUT_CARTESIAN) return no("only Cartesian input is on the tensor-core path");
@@ -847,18 +1071,42 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
         if (net.nodes[l] < 64) return no("hidden layers narrower than 64 nodes are not a dense contraction worth the tensor pipe");
     if (!encode_fn()) return no("cuTensorMapEncodeTiled is not available from this driver");
     if ((size_t) net.nodes[0] * sizeof(float) > 200 * 1024) return no("input layer too wide for the prep kernel's shared memory");
-    if (cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(prep_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(prep_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return no("cannot configure the prep kernel");
     TensorPlan* t = new TensorPlan();
     t->L = L;
+    t->kind = kind;
     if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
     if (const char* env = getenv("ANNF_GEMM_SPLIT_SHORTK")) t->force_split = atoi(env);
     if (const char* env = getenv("ANNF_TENSOR_DRY")) t->dry = atoi(env);
+    if (const char* env = getenv("ANNF_TENSOR_CHUNK")) t->chunk = std::max(1, std::min(64, atoi(env)));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    for (int l = 0; l < L; l++) { t->nodes[l] = net.nodes[l]; t->ld[l] = round_up(net.nodes[l], 4); }
+    const int ld_unit = kind == KIND_F16 ? 8 : 4;               // rows are 16-byte multiples (TMA global stride)
+    for (int l = 0; l < L; l++) { t->nodes[l] = net.nodes[l]; t->ld[l] = round_up(net.nodes[l], ld_unit); }
     for (int l = 0; l + 1 < L; l++) t->types[l] = net.types[l];
+    // norms for the magnitude bounds of KIND_F16 (ExpChain): forward max row L1 norm and max |bias|, backward max column L1 norm
+    for (int l = 0; l + 1 < L; l++) {
+        const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
+        std::vector<double> col(n_in, 0.0);
+        double row_max = 0.0, b_max = 0.0;
+        for (int j = 0; j < n_out; j++) {
+            double row = 0.0;
+            for (int i = 0; i < n_in; i++) {
+                const double a = std::fabs(coeff[l][(size_t) j * n_in + i]);
+                row += a;
+                col[i] += a;
+            }
+            row_max = std::max(row_max, row);
+            b_max = std::max(b_max, std::fabs(bias64[net.b_off[l] + j]));
+        }
+        // 1 % head-room covers the fp32 arithmetic of the bound itself
+        t->chain.fwd_gain[l] = (float) (1.01 * row_max);
+        t->chain.fwd_bias[l] = (float) (1.01 * b_max);
+        t->chain.bwd_gain[l] = (float) (1.01 * *std::max_element(col.begin(), col.end()));
+    }
     for (int l = 0; l + 2 < L; l++) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
         std::vector<float> w((size_t) n_out * t->ld[l], 0.f), wt((size_t) n_in * t->ld[l + 1], 0.f);
@@ -873,7 +1121,8 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
                 wt[(size_t) i * t->ld[l + 1] + j] = l == 0 ? (float) (-(v - wsum[i % 3] / net.n_sel) / net.scale) : (float) v;
             }
         }
-        if (upload_pair(w, &t->w_hi[l], &t->w_lo[l]) != cudaSuccess || upload_pair(wt, &t->wt_hi[l], &t->wt_lo[l]) != cudaSuccess) {
+        if (upload_pair(kind, w, n_out, t->ld[l], &t->w_hi[l], &t->w_lo[l], &t->w_exp[l]) != cudaSuccess ||
+            upload_pair(kind, wt, n_in, t->ld[l + 1], &t->wt_hi[l], &t->wt_lo[l], &t->wt_exp[l]) != cudaSuccess) {
             tensor_plan_destroy(t);
             return no("out of device memory for the tensor-core weight copies");
         }
@@ -888,22 +1137,33 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     return t;
 }
 
-static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView& net, int R) {
+int tensor_plan_kind(const TensorPlan* t) { return t->kind; }
+
+// Sizes one activation-buffer set for R replicas (rows padded to 128).  Called from tensor_plan_reserve (annf_create /
+// annf_reserve) and, when a batch is larger than anything reserved, from tensor_plan_run: the buffers are zeroed ON `stream`,
+// so the kernels enqueued right after on the same stream are ordered behind the zeroing.
+static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView& net, int R, cudaStream_t stream) {
     if (R <= t->cap) return cudaSuccess;
+    // a growing batch: make sure nothing still reads the old buffers (a rare event, never on the per-step path once warm)
+    cudaError_t err = t->cap > 0 ? cudaDeviceSynchronize() : cudaSuccess;
+    if (err != cudaSuccess) return err;
     free_activations(t);
     const int cap = round_up(R, BM);
-    const int L = plan->L;
-    auto alloc = [&](float** p, int ld) {
-        cudaError_t e = cudaMalloc((void**) p, sizeof(float) * (size_t) cap * ld);
-        if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(float) * (size_t) cap * ld);
+    const int L = plan->L, kind = plan->kind;
+    const size_t esz = kind == KIND_F16 ? 2 : 4;
+    auto alloc = [&](void** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, stream);
         return e;
     };
-    cudaError_t err = cudaSuccess;
     for (int l = 0; l + 1 < L && err == cudaSuccess; l++) {
-        err = alloc(&t->x_hi[l], plan->ld[l]);
-        if (err == cudaSuccess) err = alloc(&t->x_lo[l], plan->ld[l]);
-        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_hi[l], plan->ld[l]);
-        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], plan->ld[l]);
+        const size_t bytes = esz * (size_t) cap * plan->ld[l];
+        err = alloc(&t->x_hi[l], bytes);
+        if (err == cudaSuccess) err = alloc(&t->x_lo[l], bytes);
+        if (err == cudaSuccess) err = alloc((void**) &t->x_exp[l], sizeof(int) * cap);
+        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_hi[l], bytes);
+        if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], bytes);
+        if (l >= 1 && err == cudaSuccess) err = alloc((void**) &t->d_exp[l], sizeof(int) * cap);
     }
     if (err != cudaSuccess) return err;
     t->cap = cap;
@@ -913,37 +1173,48 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         GemmOp op;
         memset(&op, 0, sizeof(op));
         const int K = plan->nodes[l], N = plan->nodes[l + 1];
-        bool ok = make_map(&op.a_hi, t->x_hi[l], cap, K, plan->ld[l], BM) && make_map(&op.a_lo, t->x_lo[l], cap, K, plan->ld[l], BM) &&
-                  make_map(&op.a_hi64, t->x_hi[l], cap, K, plan->ld[l], BM / 2) && make_map(&op.a_lo64, t->x_lo[l], cap, K, plan->ld[l], BM / 2) &&
-                  make_map(&op.b_hi, plan->w_hi[l], N, K, plan->ld[l], 128) && make_map(&op.b_lo, plan->w_lo[l], N, K, plan->ld[l], 128) &&
-                  make_map(&op.b_hi64, plan->w_hi[l], N, K, plan->ld[l], 64) && make_map(&op.b_lo64, plan->w_lo[l], N, K, plan->ld[l], 64);
+        bool ok = make_map(&op.a_hi, kind, t->x_hi[l], cap, K, plan->ld[l], BM) && make_map(&op.a_lo, kind, t->x_lo[l], cap, K, plan->ld[l], BM) &&
+                  make_map(&op.a_hi64, kind, t->x_hi[l], cap, K, plan->ld[l], BM / 2) && make_map(&op.a_lo64, kind, t->x_lo[l], cap, K, plan->ld[l], BM / 2) &&
+                  make_map(&op.b_hi, kind, plan->w_hi[l], N, K, plan->ld[l], 128) && make_map(&op.b_lo, kind, plan->w_lo[l], N, K, plan->ld[l], 128) &&
+                  make_map(&op.b_hi64, kind, plan->w_hi[l], N, K, plan->ld[l], 64) && make_map(&op.b_lo64, kind, plan->w_lo[l], N, K, plan->ld[l], 64);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
         op.p.epi = plan->types[l] == ANNF_TANH ? EPI_BIAS_TANH : EPI_BIAS_LINEAR;
         op.p.bias = net.b32 + net.b_off[l];
         op.p.out_hi = t->x_hi[l + 1]; op.p.out_lo = t->x_lo[l + 1]; op.p.ld_out = plan->ld[l + 1];
-        snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] fwd%d tf32x3", N, K, l);
+        op.p.a_exp = t->x_exp[l]; op.p.b_exp = plan->w_exp[l]; op.p.out_exp = t->x_exp[l + 1];
+        snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] fwd%d %s", N, K, l, kind == KIND_F16 ? "f16x3" : "tf32x3");
         t->fwd.push_back(op);
     }
     for (int l = L - 3; l >= 0; l--) {                // backward: D_l = (D_{l+1} W_l) (.) act'(X_l);  l = 0 -> G0
         GemmOp op;
         memset(&op, 0, sizeof(op));
         const int K = plan->nodes[l + 1], N = plan->nodes[l];
-        bool ok = make_map(&op.a_hi, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM) && make_map(&op.a_lo, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM) &&
-                  make_map(&op.a_hi64, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM / 2) && make_map(&op.a_lo64, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM / 2) &&
-                  make_map(&op.b_hi, plan->wt_hi[l], N, K, plan->ld[l + 1], 128) && make_map(&op.b_lo, plan->wt_lo[l], N, K, plan->ld[l + 1], 128) &&
-                  make_map(&op.b_hi64, plan->wt_hi[l], N, K, plan->ld[l + 1], 64) && make_map(&op.b_lo64, plan->wt_lo[l], N, K, plan->ld[l + 1], 64);
+        bool ok = make_map(&op.a_hi, kind, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM) && make_map(&op.a_lo, kind, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM) &&
+                  make_map(&op.a_hi64, kind, t->d_hi[l + 1], cap, K, plan->ld[l + 1], BM / 2) && make_map(&op.a_lo64, kind, t->d_lo[l + 1], cap, K, plan->ld[l + 1], BM / 2) &&
+                  make_map(&op.b_hi, kind, plan->wt_hi[l], N, K, plan->ld[l + 1], 128) && make_map(&op.b_lo, kind, plan->wt_lo[l], N, K, plan->ld[l + 1], 128) &&
+                  make_map(&op.b_hi64, kind, plan->wt_hi[l], N, K, plan->ld[l + 1], 64) && make_map(&op.b_lo64, kind, plan->wt_lo[l], N, K, plan->ld[l + 1], 64);
         if (!ok) return cudaErrorInvalidValue;
         op.p.N = N; op.p.K = K;
+        op.p.a_exp = t->d_exp[l + 1]; op.p.b_exp = plan->wt_exp[l];
         if (l == 0) {
             op.p.epi = EPI_FORCE;                     // out_hi / ld_out / sel_atoms are per call (launch_gemm)
         } else {
             op.p.epi = plan->types[l - 1] == ANNF_TANH ? EPI_TANH_GRAD : EPI_LINEAR_GRAD;
-            op.p.aux_hi = t->x_hi[l]; op.p.aux_lo = t->x_lo[l]; op.p.ld_aux = plan->ld[l];
-            op.p.out_hi = t->d_hi[l]; op.p.out_lo = t->d_lo[l]; op.p.ld_out = plan->ld[l];
+            op.p.aux_hi = t->x_hi[l]; op.p.aux_lo = t->x_lo[l]; op.p.ld_aux = plan->ld[l]; op.p.aux_exp = t->x_exp[l];
+            op.p.out_hi = t->d_hi[l]; op.p.out_lo = t->d_lo[l]; op.p.ld_out = plan->ld[l]; op.p.out_exp = t->d_exp[l];
         }
-        snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] bwd%d tf32x3", N, K, l);
+        snprintf(op.name, sizeof(op.name), "gemm[Rx%dx%d] bwd%d %s", N, K, l, kind == KIND_F16 ? "f16x3" : "tf32x3");
         t->bwd.push_back(op);
+    }
+    return cudaSuccess;
+}
+
+// Pre-sizes both activation-buffer sets for batches of up to R replicas, so that no later call allocates.
+cudaError_t tensor_plan_reserve(TensorPlan* plan, const NetView& net, int R, cudaStream_t stream) {
+    for (PlanSlot& slot : plan->slots) {
+        const cudaError_t err = ensure_capacity(plan, &slot, net, R, stream);
+        if (err != cudaSuccess) return err;
     }
     return cudaSuccess;
 }
@@ -980,24 +1251,24 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int BN, int S, int CG, int NX = 1>
+template <int KIND, int BN, int S, int CG, int NX = 1>
 static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CG>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t err = cudaFuncSetAttribute(gemm3x_kernel<KIND, BN, S, CG, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (err != cudaSuccess) return err;
         if (CG * NX * S > 8) {
-            err = cudaFuncSetAttribute(gemm3x_kernel<BN, S, CG, NX>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            err = cudaFuncSetAttribute(gemm3x_kernel<KIND, BN, S, CG, NX>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (err != cudaSuccess) return err;
         }
         configured[dev] = true;
     }
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM * CG - 1) / (BM * CG);
     constexpr bool kBox64 = Cfg::kBRows < 128;
-    return launch_pdl(gemm3x_kernel<BN, S, CG, NX>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG * NX, S,
+    return launch_pdl(gemm3x_kernel<KIND, BN, S, CG, NX>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG * NX, S,
                       NX == 2 ? op.a_hi64 : op.a_hi, NX == 2 ? op.a_lo64 : op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo, p);
 }
 
@@ -1007,11 +1278,14 @@ static int pick_split(int tiles, int k_blocks, int sm_count) {
     return s;
 }
 
+template <int KIND>
 static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStream_t stream, const NetView& net,
                                float* forces, int atoms_per_replica) {
+    constexpr int BK = KindOf<KIND>::kBlockElems;
     GemmParams p = op.p;
     p.M = R;
     p.dry = t->dry;
+    p.chunk = t->chunk;
     if (p.epi == EPI_FORCE) {
         p.out_hi = forces;
         p.ld_out = 3 * atoms_per_replica;
@@ -1044,10 +1318,10 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         if (s == 4 && tiles / 2 > 15) s = 3;
         if (const char* env = getenv("ANNF_GEMM_NX_SPLIT")) s = atoi(env);
         switch (s) {
-        case 4: return launch_gemm_t<128, 4, 1, 2>(op, p, stream);
-        case 3: return launch_gemm_t<128, 3, 1, 2>(op, p, stream);
-        case 2: return launch_gemm_t<128, 2, 1, 2>(op, p, stream);
-        default: return launch_gemm_t<128, 1, 1, 2>(op, p, stream);
+        case 4: return launch_gemm_t<KIND, 128, 4, 1, 2>(op, p, stream);
+        case 3: return launch_gemm_t<KIND, 128, 3, 1, 2>(op, p, stream);
+        case 2: return launch_gemm_t<KIND, 128, 2, 1, 2>(op, p, stream);
+        default: return launch_gemm_t<KIND, 128, 1, 1, 2>(op, p, stream);
         }
     }
     if (mode == 132) mode = 128;
@@ -1058,9 +1332,9 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         int s = std::min(4, pick_split(pair_ctas, kb, t->sm_count));
         if (t->force_split > 0 && kb <= 32) s = std::min(4, t->force_split);
         switch (s) {
-        case 4: return launch_gemm_t<128, 4, 2>(op, p, stream);
-        case 2: return launch_gemm_t<128, 2, 2>(op, p, stream);
-        default: return launch_gemm_t<128, 1, 2>(op, p, stream);
+        case 4: return launch_gemm_t<KIND, 128, 4, 2>(op, p, stream);
+        case 2: return launch_gemm_t<KIND, 128, 2, 2>(op, p, stream);
+        default: return launch_gemm_t<KIND, 128, 1, 2>(op, p, stream);
         }
     }
     if (mode == 512) {
@@ -1069,16 +1343,16 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         if (t->force_split > 0 && kb <= 32) s = t->force_split;
         if (s == 8 && !t->no_cluster16) {
             // 2 x 8 = 16 CTAs is a non-portable cluster size: if this device cannot co-schedule it, remember and use 2 x 4
-            const cudaError_t e = launch_gemm_t<256, 8, 2>(op, p, stream);
+            const cudaError_t e = launch_gemm_t<KIND, 256, 8, 2>(op, p, stream);
             if (e == cudaSuccess) return e;
             cudaGetLastError();
             t->no_cluster16 = true;
         }
         if (s == 8) s = 4;
         switch (s) {
-        case 4: return launch_gemm_t<256, 4, 2>(op, p, stream);
-        case 2: return launch_gemm_t<256, 2, 2>(op, p, stream);
-        default: return launch_gemm_t<256, 1, 2>(op, p, stream);
+        case 4: return launch_gemm_t<KIND, 256, 4, 2>(op, p, stream);
+        case 2: return launch_gemm_t<KIND, 256, 2, 2>(op, p, stream);
+        default: return launch_gemm_t<KIND, 256, 1, 2>(op, p, stream);
         }
     }
     const int bn = mode == 256 ? 256 : 128;
@@ -1087,26 +1361,24 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
     if (t->force_split > 0 && kb <= 32) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
     if (bn == 256) {
         switch (s) {
-        case 8: return launch_gemm_t<256, 8, 1>(op, p, stream);
-        case 4: return launch_gemm_t<256, 4, 1>(op, p, stream);
-        case 2: return launch_gemm_t<256, 2, 1>(op, p, stream);
-        default: return launch_gemm_t<256, 1, 1>(op, p, stream);
+        case 8: return launch_gemm_t<KIND, 256, 8, 1>(op, p, stream);
+        case 4: return launch_gemm_t<KIND, 256, 4, 1>(op, p, stream);
+        case 2: return launch_gemm_t<KIND, 256, 2, 1>(op, p, stream);
+        default: return launch_gemm_t<KIND, 256, 1, 1>(op, p, stream);
         }
     }
     switch (s) {
-    case 8: return launch_gemm_t<128, 8, 1>(op, p, stream);
-    case 4: return launch_gemm_t<128, 4, 1>(op, p, stream);
-    case 2: return launch_gemm_t<128, 2, 1>(op, p, stream);
-    default: return launch_gemm_t<128, 1, 1>(op, p, stream);
+    case 8: return launch_gemm_t<KIND, 128, 8, 1>(op, p, stream);
+    case 4: return launch_gemm_t<KIND, 128, 4, 1>(op, p, stream);
+    case 2: return launch_gemm_t<KIND, 128, 2, 1>(op, p, stream);
+    default: return launch_gemm_t<KIND, 128, 1, 1>(op, p, stream);
     }
 }
 
-cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, int R, const float* coords,
-                            int atoms_per_replica, const float* centers, float* forces, double* energies,
-                            cudaStream_t stream, long long* launches, int slot_index) {
-    PlanSlot* sl = &t->slots[slot_index % kPlanSlots];
-    cudaError_t err = ensure_capacity(t, sl, net, R);
-    if (err != cudaSuccess) return err;
+template <int KIND>
+static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net, int R, const float* coords,
+                              int atoms_per_replica, const float* centers, float* forces, double* energies,
+                              cudaStream_t stream, long long* launches, PlanSlot* sl) {
     const int L = t->L;
     char name[64];
     auto timed = [&](const char* nm, auto&& fn) {
@@ -1116,29 +1388,42 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
         if (launches) (*launches)++;
         return e;
     };
-    err = timed("prep_kernel", [&] {
+    ExpChain chain = t->chain;
+    for (int l = 0; l < kMaxLayers; l++) { chain.x_exp[l] = sl->x_exp[l]; chain.d_exp[l] = sl->d_exp[l]; }
+    cudaError_t err = timed("prep_kernel", [&] {
         const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
                                (t->dry ? 2 : 0);
-        return launch_pdl(prep_kernel, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
-                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous);
+        return launch_pdl(prep_kernel<KIND>, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
+                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : sl->fwd) {
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
-        err = timed(name, [&] { return launch_gemm(t, op, R, stream, net, nullptr, 0); });
+        err = timed(name, [&] { return launch_gemm<KIND>(t, op, R, stream, net, nullptr, 0); });
         if (err != cudaSuccess) return err;
     }
     err = timed("head_kernel", [&] {
-        return launch_pdl(head_kernel, dim3(R), dim3(kHeadThreads), 0, stream, 1, 0, net, t->dry ? -R : R, centers, (const float*) sl->x_hi[L - 2],
-                          (const float*) sl->x_lo[L - 2], t->ld[L - 2], sl->d_hi[L - 2], sl->d_lo[L - 2], energies);
+        return launch_pdl(head_kernel<KIND>, dim3(R), dim3(kHeadThreads), 0, stream, 1, 0, net, t->dry ? -R : R, centers, (const void*) sl->x_hi[L - 2],
+                          (const void*) sl->x_lo[L - 2], t->ld[L - 2], sl->d_hi[L - 2], sl->d_lo[L - 2], energies, chain);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : sl->bwd) {
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
-        err = timed(name, [&] { return launch_gemm(t, op, R, stream, net, forces, atoms_per_replica); });
+        err = timed(name, [&] { return launch_gemm<KIND>(t, op, R, stream, net, forces, atoms_per_replica); });
         if (err != cudaSuccess) return err;
     }
     return cudaSuccess;
+}
+
+cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, int R, const float* coords,
+                            int atoms_per_replica, const float* centers, float* forces, double* energies,
+                            cudaStream_t stream, long long* launches, int slot_index) {
+    PlanSlot* sl = &t->slots[slot_index % kPlanSlots];
+    cudaError_t err = ensure_capacity(t, sl, net, R, stream);
+    if (err != cudaSuccess) return err;
+    if (t->kind == KIND_F16)
+        return plan_run_t<KIND_F16>(t, prof, net, R, coords, atoms_per_replica, centers, forces, energies, stream, launches, sl);
+    return plan_run_t<KIND_TF32>(t, prof, net, R, coords, atoms_per_replica, centers, forces, energies, stream, launches, sl);
 }
 
 }  // namespace annf

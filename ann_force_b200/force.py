@@ -180,6 +180,10 @@ class ANN_Force:
                 raise ValueError("Cartesian input: 3*len(index_of_backbone_atoms) must equal num_of_nodes[0]")
             if any(i < 1 for i in self._index_of_backbone_atoms):
                 raise ValueError("index_of_backbone_atoms is 1-based")
+            # the reference accumulates per list entry (ANN_ReferenceKernels.cpp:401); the batched kernels write one force
+            # row per selected atom, so a repeated atom is rejected instead of being evaluated two different ways
+            if len(set(self._index_of_backbone_atoms)) != len(self._index_of_backbone_atoms):
+                raise ValueError("index_of_backbone_atoms lists an atom more than once")
         elif t == INPUT_COS_SIN_OF_DIHEDRALS:
             if 2 * len(self._dihedrals) != self._num_of_nodes[0]:
                 raise ValueError("dihedral input: 2*number of dihedrals must equal num_of_nodes[0]")

@@ -110,8 +110,14 @@ void ANN_Force::validate(int numParticles) const {
     if (data_type_in_input_layer == 1) {
         if (3 * (int) index_of_backbone_atoms.size() != num_of_nodes[0])
             throw OpenMMException("ANN_Force: Cartesian input needs 3 * len(index_of_backbone_atoms) == num_of_nodes[0]");
-        for (int a : index_of_backbone_atoms)
+        std::vector<char> seen((size_t) numParticles + 1, 0);
+        for (int a : index_of_backbone_atoms) {
             if (a < 1 || a > numParticles) throw OpenMMException("ANN_Force: index_of_backbone_atoms is 1-based and must lie inside the System");
+            // the reference accumulates per list entry (ANN_ReferenceKernels.cpp:401); the batched kernels write one force row
+            // per selected atom, so a repeated atom is rejected instead of being evaluated two different ways
+            if (seen[a]) throw OpenMMException("ANN_Force: index_of_backbone_atoms lists an atom more than once");
+            seen[a] = 1;
+        }
     } else if (data_type_in_input_layer == 0) {
         if (2 * (int) list_of_index_of_atoms_forming_dihedrals.size() != num_of_nodes[0])
             throw OpenMMException("ANN_Force: dihedral input needs 2 * number of dihedrals == num_of_nodes[0]");

@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU (default: the workload's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp64", "fp32", "tf32x3"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp64", "fp32", "tf32x3", "f16x3"])
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run comparison of sampled replicas with the CPU reference")
@@ -452,24 +452,33 @@ def main():
         name, rec = dominant
         avg_ms = rec["total_ms"] / max(rec["launches"], 1)
         kflops = kernel_flops(name, nodes, R, flops_eval)
-        if name.startswith("gemm["):
-            # tcgen05 kind::tf32 path (3xTF32): dense TF32 peak
-            peak = peaks["bf16_tflops_sustained"] / 2.0
-            peak_source = ("%s bf16_tflops_sustained / 2 (dense TF32 = half the bf16 rate; a 3xTF32 kernel tops out at frac 1/3)"
+        latency_bound = args.workload != "c5"
+        if name.startswith("gemm[") and "f16x3" in name:
+            # tcgen05 kind::f16 on fp16 pairs: the dense fp16/bf16 tensor peak.  Burst figure: the kernel is timed alone,
+            # one event pair per launch.  A three-product kernel tops out at frac 1/3.
+            bound = "tensor"
+            peak = peaks["bf16_tflops"]
+            peak_source = ("%s bf16_tflops (burst; dense fp16 = the bf16 rate).  Three MMAs per product: ceiling frac 1/3" % peaks["source"])
+        elif name.startswith("gemm["):
+            bound = "tensor"
+            peak = peaks["bf16_tflops"] / 2.0
+            peak_source = ("%s bf16_tflops (burst) / 2 (dense TF32 = half the bf16 rate).  Three MMAs per product: ceiling frac 1/3"
                            % peaks["source"])
         elif "f32" in name:
+            bound = "latency" if latency_bound else "fp32"
             clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
             peak = 128.0 * 2.0 * info["sm_count"] * clk / 1e12
             peak_source = "FP32 FMA pipe: 128 FMA/clk/SM x %d SMs x %.0f MHz" % (info["sm_count"], clk / 1e6)
         else:
             # fp64 kernels: the FP64 pipe.  DFMA and DMMA (mma.sync.m8n8k4.f64) both issue at 64 FMA/clk/SM on B200
             # (measured with tools/fp64_probe.cu, profiles/r01_fp64_probe.txt); peak = 64 x 2 x SMs x SM clock under load
+            bound = "latency" if (single or args.workload == "c3") else "fp64"
             clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
             peak = 64.0 * 2.0 * info["sm_count"] * clk / 1e12
-            peak_source = "FP64 pipe: 64 FMA/clk/SM (tools/fp64_probe.cu, profiles/r01_fp64_probe.txt) x %d SMs x %.0f MHz" % (
-                info["sm_count"], clk / 1e6)
+            peak_source = "FP64 pipe: 64 FMA/clk/SM (tools/fp64_probe.cu: %s) x %d SMs x %.0f MHz" % (
+                fp64_probe_line(), info["sm_count"], clk / 1e6)
         achieved = kflops / (avg_ms * 1e-3) / 1e12
-        roofline = dict(bound="tensor", kernel=name, achieved=achieved, peak=peak, unit="TFLOP/s",
+        roofline = dict(bound=bound, kernel=name, achieved=achieved, peak=peak, unit="TFLOP/s",
                         frac=achieved / peak, traffic=load_traffic(name),
                         avg_launch_ms=avg_ms, launches=rec["launches"],
                         share_of_step=rec["total_ms"] / max(sum(v["total_ms"] for v in times.values()), 1e-12),
@@ -503,7 +512,7 @@ def main():
     steps_per_s_per_replica = steps / (gpu_ms_max * 1e-3)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=gpu_ms_max / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"fp64": "f64", "fp32": "f32", "tf32x3": "tf32x3 (fp32 accumulate)"}[info["precision_single" if single else "precision_batched"]],
+                dtype={"fp64": "f64", "fp32": "f32", "tf32x3": "tf32x3 (fp32 accumulate)", "f16x3": "f16x3 (scaled fp16 pairs, fp32 accumulate)"}[info["precision_single" if single else "precision_batched"]],
                 data="synthetic", config=config,
                 path=info["batched_path"] if not single else "single-replica kernel (%s)" % info["single_path"],
                 timing=dict(windows=int(n_windows), steps_per_window=steps, ms_per_step_min=float(window_ms.min()) / steps,
@@ -551,6 +560,23 @@ def parity_check(kernel, force, single, ctx, coords0, centers, centers_np, n_sam
     return dict(n=int(len(idx)), energy_rel_max=float(e_rel.max()), energy_rel_median=float(np.median(e_rel)),
                 force_rel_maxnorm=float(f_rel.max()), force_rel_maxnorm_median=float(np.median(f_rel)),
                 against="oracle/_ref (reference CPU kernel, fp64)" if evaluate is not port.evaluate else "oracle/ann_oracle.c (fp64 restatement)")
+
+
+def fp64_probe_line():
+    """One-line result of tools/fp64_probe (DFMA / DMMA issue rate per SM), run here if the binary travelled, else the
+    committed round-1 measurement."""
+    exe = os.path.join(ROOT, "tools", "_build", "fp64_probe")
+    try:
+        import subprocess
+        out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=60).stdout.splitlines()
+        best = {}
+        for line in out:
+            parts = line.split()
+            if len(parts) > 3 and parts[0] in ("DFMA", "DMMA") and parts[-1] == "FMA/clk/SM":
+                best[parts[0]] = max(best.get(parts[0], 0.0), float(parts[-2]))
+        return "measured in this run: DFMA %.1f, DMMA %.1f FMA/clk/SM at best" % (best.get("DFMA", 0.0), best.get("DMMA", 0.0))
+    except Exception:       # noqa: BLE001
+        return "profiles/r01_fp64_probe.txt"
 
 
 def kernel_flops(name, nodes, R, flops_eval):

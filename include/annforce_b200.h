@@ -11,8 +11,18 @@
  * Arithmetic semantics are those of the reference CPU kernel
  *     ReferenceCalcANN_ForceKernel::candidate_2   /root/reference/platforms/reference/ANN_ReferenceKernels.cpp:122-171
  *
- * All device work is enqueued on the caller's stream; no call synchronises or allocates per step
- * except annf_eval_batched_host (the host-buffer convenience entry, which owns its stream).
+ * All device work is enqueued on the caller's stream.  Which calls wait or allocate:
+ *   annf_create, annf_destroy            allocate / free, synchronise the device
+ *   annf_eval_openmm                     never waits, never allocates
+ *   annf_eval_batched                    never waits; on the tensor-core path (batched_path 1) the handle owns activation
+ *                                        scratch sized for the largest batch seen so far: a LARGER batch than any before
+ *                                        re-allocates it (device-synchronising once).  annf_reserve sizes it up front, after
+ *                                        which no evaluation allocates.  Because that scratch belongs to the handle, two
+ *                                        annf_eval_batched calls on DIFFERENT streams must not be in flight at once on one
+ *                                        handle (use one handle per stream, as one OpenMM Context has one stream).
+ *   annf_update_parameters               stream-ordered, returns without waiting (waits only if 4 earlier updates are still queued)
+ *   annf_eval_batched_host               the host-buffer convenience entry: owns its streams, waits for the results
+ *   annf_debug_*                         synchronise (diagnostic builds only)
  * A handle may be used from one host thread at a time; different handles are independent.
  */
 #ifndef ANNFORCE_B200_H_
@@ -47,9 +57,11 @@ enum { ANNF_INPUT_DIHEDRAL_COS_SIN = 0, ANNF_INPUT_CARTESIAN = 1, ANNF_INPUT_PAI
  *   FP64    everything fp64 (B200 runs fp64 FMA at half the fp32 rate): parity to ~1e-12
  *   FP32    hidden-layer contractions in fp32 FMA
  *   TF32X3  hidden-layer contractions on tcgen05 tensor cores, 3xTF32 split, fp32 accumulate in TMEM
- *   AUTO    FP64 for the single-replica OpenMM entry and for small networks; TF32X3 for layers wide
+ *   F16X3   the same 11 + 11-bit operand split carried in fp16 pairs with per-row power-of-two scales
+ *           (tcgen05 kind::f16): identical significand budget, half the operand bytes, twice the MMA rate
+ *   AUTO    FP64 for the single-replica OpenMM entry and for small networks; F16X3 for layers wide
  *           enough to be a real dense contraction; FP32 otherwise */
-enum { ANNF_PREC_AUTO = 0, ANNF_PREC_FP64 = 1, ANNF_PREC_FP32 = 2, ANNF_PREC_TF32X3 = 3 };
+enum { ANNF_PREC_AUTO = 0, ANNF_PREC_FP64 = 1, ANNF_PREC_FP32 = 2, ANNF_PREC_TF32X3 = 3, ANNF_PREC_F16X3 = 4 };
 
 typedef enum {
     ANNF_OK = 0,
@@ -113,10 +125,15 @@ ANNF_API annf_status annf_destroy(annf_handle h);
 ANNF_API annf_status annf_get_info(annf_handle h, annf_info* info);
 
 /* copyParametersToContext(): move the umbrella centre and force constant on the device.
- * Ordered on `stream` (and complete on return); takes effect for evaluations enqueued after it.  (Both reference platforms
+ * Ordered on `stream` (the host arrays are copied before the call returns; the call does not wait for the device); takes
+ * effect for evaluations enqueued on `stream` after it.  (Both reference platforms
  * leave this an empty stub: ANN_ReferenceKernels.cpp:96-111, CudaANN_Kernels.cpp:371-395.) */
 ANNF_API annf_status annf_update_parameters(annf_handle h, const double* potential_center, int32_t num_center,
                                    double force_constant, void* stream);
+
+/* Pre-size the per-handle scratch of annf_eval_batched for batches of up to max_replicas, so that no later evaluation
+ * allocates (see the preamble).  A no-op on paths that keep no per-batch scratch. */
+ANNF_API annf_status annf_reserve(annf_handle h, int32_t max_replicas, void* stream);
 
 /* OpenMM's CUDA platform re-orders atoms; atom_index_dev[slot] = original atom index (device
  * pointer, CudaContext::getAtomIndexArray()).  Call once after creation and from a reorder
@@ -146,8 +163,10 @@ ANNF_API annf_status annf_eval_openmm(annf_handle h, const void* posq, const voi
 ANNF_API annf_status annf_eval_batched(annf_handle h, int32_t num_replicas, const float* coords, int32_t atoms_per_replica,
                               const float* centers, float* forces, double* energies, void* stream);
 
-/* The same with HOST buffers: stages through pinned memory, copies host->device, evaluates, copies
- * forces and energies device->host and waits.  forces_host is overwritten completely (zeros for atoms
+/* The same with HOST buffers: copies host->device in chunks, evaluates each chunk as it lands, copies forces and energies
+ * device->host and waits.  The copies are cudaMemcpyAsync straight from / to the caller's buffers: with PINNED (page-locked)
+ * buffers they overlap the evaluation of neighbouring chunks; with pageable buffers the results are the same but every copy
+ * is staged by the driver and the overlap is lost (measured cost in DESIGN.md 5).  forces_host is overwritten completely (zeros for atoms
  * outside the selection).  This is the end-to-end entry bench.py times. */
 ANNF_API annf_status annf_eval_batched_host(annf_handle h, int32_t num_replicas, const float* coords_host,
                                    int32_t atoms_per_replica, const float* centers_host, float* forces_host,

@@ -88,6 +88,16 @@ def test_no_cpu_fallback():
     assert _capi.lib().annf_create(C.byref(desc), C.byref(handle)) == _capi.ERR_INVALID
     desc.struct_size = 4
     assert _capi.lib().annf_create(C.byref(desc), C.byref(handle)) == _capi.ERR_INVALID
+    # a selected atom listed twice: the reference would sum its two contributions (ANN_ReferenceKernels.cpp:401), the batched
+    # kernels write one row per selected atom -> rejected up front, in the C ABI and in both validate() mirrors
+    desc.struct_size = C.sizeof(_capi.Desc)
+    desc.num_center = 2
+    atoms[3] = atoms[5]
+    assert _capi.lib().annf_create(C.byref(desc), C.byref(handle)) == _capi.ERR_INVALID
+    assert b"more than once" in _capi.lib().annf_last_error()
+    force.set_index_of_backbone_atoms([1, 2, 3, 4, 5, 6, 6])
+    with pytest.raises(ValueError):
+        force.validate()
 
 
 def test_product_never_imports_the_oracle():

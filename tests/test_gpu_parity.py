@@ -17,6 +17,7 @@ from oracle import port
 
 pytestmark = pytest.mark.gpu
 
+TENSOR_KINDS = ["tf32x3", "f16x3"]     # operand container of the tcgen05 path
 E_RTOL = 1e-6      # north_star energy bar
 F_RTOL = 1e-4      # north_star force bar (relative max-norm)
 FIXED_POINT_ULP = 2.0 ** -32   # OpenMM's force buffer resolution, kJ/mol/nm
@@ -229,7 +230,7 @@ def test_wide_network_properties_and_sampled_parity():
     pos = synthetic.make_positions(cfg["atoms"], R)
     cen = synthetic.make_centers(force, R)
     e, f, kernel = run_batched(force, pos, cen, precision="auto")
-    assert kernel.info()["batched_path"] == "tensor" and kernel.info()["precision_batched"] == "tf32x3"
+    assert kernel.info()["batched_path"] == "tensor" and kernel.info()["precision_batched"] == "f16x3"
     sample = [0, 11, 23]
     e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
     tol_e = 2e-5 if kernel.info()["precision_batched"] != "fp64" else 1e-10
@@ -256,8 +257,9 @@ def test_wide_network_properties_and_sampled_parity():
     ([1536, 256, 256, 2], ["Tanh", "Tanh", "Linear"], 384),      # three M tiles
     ([4500, 512, 512, 8], ["Tanh", "Tanh", "Tanh"], 600),        # BASELINE C5 widths: CTA-pair GEMMs, 2 x 8 clusters, ragged M
 ])
-def test_tensor_core_path_matches_oracle(nodes, types, R):
-    """tcgen05 3xTF32 path.  Stated tolerance (BASELINE config 5 "tensor-core dense-contraction path, stated
+@pytest.mark.parametrize("precision", TENSOR_KINDS)
+def test_tensor_core_path_matches_oracle(nodes, types, R, precision):
+    """tcgen05 path with the 11 + 11-bit operand split, carried as TF32 pairs (tf32x3) or as scaled fp16 pairs (f16x3).  Stated tolerance (BASELINE config 5 "tensor-core dense-contraction path, stated
     tolerance"), worst replica: energy 2e-5 relative for Tanh/Linear/Softmax outputs and 2e-4 for Circular outputs
     (an angle error d_theta costs k*Delta*d_theta, and Delta reaches pi); forces 1e-4 relative max-norm.
     The MEDIAN energy error must stay below 3e-6: a lost hi*lo term would put it near 5e-4."""
@@ -265,8 +267,8 @@ def test_tensor_core_path_matches_oracle(nodes, types, R):
     force = synthetic.make_force(nodes, types, atoms, seed=41)
     pos = synthetic.make_positions(atoms + 3, R, seed=42)
     cen = synthetic.make_centers(force, R, seed=43)
-    e, f, kernel = run_batched(force, pos, cen, precision="tf32x3")
-    assert kernel.info()["batched_path"] == "tensor"
+    e, f, kernel = run_batched(force, pos, cen, precision=precision)
+    assert kernel.info()["batched_path"] == "tensor" and kernel.info()["precision_batched"] == precision
     e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
     rel = np.abs(e - e_ref) / np.abs(e_ref)
     assert rel.max() <= (2e-4 if types[-1] == "Circular" else 2e-5), rel.max()
@@ -274,13 +276,14 @@ def test_tensor_core_path_matches_oracle(nodes, types, R):
     assert max_norm_rel(f, f_ref) <= F_RTOL
     assert np.all(f[:, atoms:, :] == 0.0)
     # run-to-run determinism (split-K reduces in a fixed order)
-    e2, f2, _ = run_batched(force, pos, cen, precision="tf32x3")
+    e2, f2, _ = run_batched(force, pos, cen, precision=precision)
     np.testing.assert_array_equal(e, e2)
     np.testing.assert_array_equal(f, f2)
 
 
+@pytest.mark.parametrize("precision", TENSOR_KINDS)
 @pytest.mark.parametrize("bn", ["128", "256", "512", "130", "132"])
-def test_tensor_core_tile_widths_agree(bn, monkeypatch):
+def test_tensor_core_tile_widths_agree(bn, precision, monkeypatch):
     """Every GEMM tile shape against the oracle — 128 wide (4 epilogue warps), 256 wide (8 epilogue warps + setmaxnreg)
     "512" = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, multicast commits), "130" = 256 x 128 CTA-pair tiles and
     "132" = 128-wide tiles whose N-neighbours share the A tile by TMA multicast — with split-K 3, 4 and 8,
@@ -289,16 +292,56 @@ def test_tensor_core_tile_widths_agree(bn, monkeypatch):
     nodes, types, R = [1200, 600, 320, 6], ["Tanh", "Tanh", "Tanh"], 150
     force = synthetic.make_force(nodes, types, 400, seed=51)
     pos = synthetic.make_positions(400, R, seed=52)
-    e, f, kernel = run_batched(force, pos, None, precision="tf32x3")
+    e, f, kernel = run_batched(force, pos, None, precision=precision)
     e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
     np.testing.assert_allclose(e, e_ref, rtol=2e-5)
     assert max_norm_rel(f, f_ref) <= F_RTOL
 
 
-def test_tensor_core_path_rejects_what_it_cannot_do():
+@pytest.mark.parametrize("precision", TENSOR_KINDS)
+def test_tensor_core_path_rejects_what_it_cannot_do(precision):
     force = synthetic.make_force([21, 40, 4], ["Tanh", "Circular"], 7, seed=1)
     with pytest.raises(_capi.ANNForceError):
-        CalcANNForce(precision="tf32x3").initialize(7, force)      # 21 and 40 are not dense-contraction shapes
+        CalcANNForce(precision=precision).initialize(7, force)      # 21 and 40 are not dense-contraction shapes
+
+
+@pytest.mark.parametrize("spread", [1.0, 1e-4, 3e3])
+def test_f16_pairs_keep_their_precision_at_any_input_magnitude(spread):
+    """fp16 has a 5-bit exponent: the f16x3 path multiplies every operand row by a power of two first.  Molecules of very
+    different extent in ONE batch (per-replica scale), a scaling factor far from 1, a Linear hidden layer (whose output
+    magnitude is only bounded, not known) and weights of very different magnitude per row must all keep the tf32x3 error."""
+    nodes, types, R = [300, 128, 64, 4], ["Linear", "Tanh", "Tanh"], 96
+    force = synthetic.make_force(nodes, types, 100, seed=61, scaling_factor=0.5 * spread)
+    rng = np.random.default_rng(62)
+    w = [np.array(c, dtype=np.float64).reshape(nodes[l + 1], nodes[l]) for l, c in enumerate(force.get_coeffients_of_connections())]
+    w[0] *= (10.0 ** rng.uniform(-2, 0, size=(nodes[1], 1)))        # rows of W0 spanning two decades
+    w[0] = w[0].astype(np.float32).astype(np.float64)
+    force.set_coeffients_of_connections([m.ravel() for m in w])
+    pos = synthetic.make_positions(100, R, seed=63).astype(np.float64) * spread
+    pos *= (10.0 ** rng.uniform(-2, 0.5, size=(R, 1, 1)))           # replicas spanning 2.5 decades in one batch
+    pos = pos.astype(np.float32)
+    cen = synthetic.make_centers(force, R, seed=64)
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    errs = {}
+    for precision in TENSOR_KINDS:
+        e, f, kernel = run_batched(force, pos, cen, precision=precision)
+        assert kernel.info()["precision_batched"] == precision
+        errs[precision] = (np.abs(e - e_ref) / np.abs(e_ref), max_norm_rel(f, f_ref))
+        assert np.all(np.isfinite(e)) and np.all(np.isfinite(f))
+    # the bar is the tf32x3 result on the same (deliberately badly scaled) problem: the containers must not differ
+    assert errs["f16x3"][0].max() <= max(2e-5, 2.0 * errs["tf32x3"][0].max()), errs
+    assert errs["f16x3"][1] <= max(F_RTOL, 2.0 * errs["tf32x3"][1]), errs
+    assert np.median(errs["f16x3"][0]) <= max(3e-6, 2.0 * np.median(errs["tf32x3"][0])), errs
+
+
+def test_f16_pairs_with_a_vanishing_gradient():
+    """dE/dz = 0 for every output: the gradient rows are all zero and their magnitude bound is 0 (no log2(0), no NaN)."""
+    nodes, types, R = [300, 128, 64, 4], ["Tanh", "Tanh", "Linear"], 5
+    force = synthetic.make_force(nodes, types, 100, seed=71)
+    pos = synthetic.make_positions(100, R, seed=72)
+    force.set_force_constant(0.0)                                   # k = 0: E = 0 and dE/dz = 0 exactly
+    e, f, _ = run_batched(force, pos, None, precision="f16x3")
+    assert np.all(e == 0.0) and np.all(f == 0.0)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -425,11 +468,12 @@ def test_large_replica_count_and_padded_rows():
     assert max_norm_rel(f[sample][:, :7], f_ref[:, :7]) <= 1e-6
 
 
-def test_tensor_path_capacity_growth_and_reuse():
+@pytest.mark.parametrize("precision", TENSOR_KINDS)
+def test_tensor_path_capacity_growth_and_reuse(precision):
     """The tensor plan re-allocates when a later call brings more replicas, and both activation-buffer sets of the
     pipelined host entry give the same answer as the device entry."""
     force = synthetic.make_force([300, 128, 64, 4], ["Tanh", "Tanh", "Tanh"], 100, seed=81)
-    kernel = CalcANNForce(precision="tf32x3")
+    kernel = CalcANNForce(precision=precision)
     kernel.initialize(100, force)
     results = []
     for R in (40, 300, 129):
