@@ -41,15 +41,35 @@ class ReplicaSharder:
         """This rank's block of a [R, ...] array (numpy or torch)."""
         return array[self.begin:self.end]
 
+    def _buffers(self, like: torch.Tensor):
+        """Send / receive buffers of the energy all-gather, allocated once per (dtype, device)."""
+        key = (like.dtype, like.device)
+        if getattr(self, "_buf_key", None) != key:
+            width = max(self.counts)
+            self._width = width
+            self._send = torch.zeros(width, dtype=like.dtype, device=like.device)
+            self._recv = torch.empty(self.world_size * width, dtype=like.dtype, device=like.device)
+            self._even = all(c == width for c in self.counts)
+            if not self._even:
+                # global replica r lives at rank(r) * width + (r - begin(rank(r))) of the padded receive buffer
+                idx = [rk * width + i for rk in range(self.world_size) for i in range(self.counts[rk])]
+                self._index = torch.tensor(idx, dtype=torch.int64, device=like.device)
+            self._buf_key = key
+        return self._send, self._recv
+
     def gather_energies(self, local_energies: torch.Tensor) -> torch.Tensor:
-        """All ranks' per-replica energies, in global replica order, on every rank (replica exchange)."""
+        """All ranks' per-replica energies, in global replica order, on every rank (replica exchange).
+
+        One `all_gather_into_tensor` over pre-allocated buffers.  With equal shards (the usual case) the local energies are
+        gathered straight from the caller's tensor and the result is a VIEW of the receive buffer, valid until the next call;
+        with unequal shards the local block is padded to the widest shard and the result is one index_select."""
         assert local_energies.numel() == self.local_count
         if self.world_size == 1:
-            return local_energies.clone()
-        width = max(self.counts)
-        padded = torch.zeros(width, dtype=local_energies.dtype, device=local_energies.device)
-        padded[: self.local_count] = local_energies
-        out = torch.empty(self.world_size * width, dtype=local_energies.dtype, device=local_energies.device)
-        dist.all_gather_into_tensor(out, padded)
-        out = out.view(self.world_size, width)
-        return torch.cat([out[r, : self.counts[r]] for r in range(self.world_size)])
+            return local_energies
+        send, recv = self._buffers(local_energies)
+        if self._even:
+            dist.all_gather_into_tensor(recv, local_energies.contiguous().view(-1))
+            return recv
+        send[: self.local_count].copy_(local_energies.view(-1))
+        dist.all_gather_into_tensor(recv, send)
+        return recv.index_select(0, self._index)

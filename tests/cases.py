@@ -89,6 +89,29 @@ def pair_distance_6_3_3():
     return f, pos
 
 
+def alanine_dipeptide_8_15_2(reference_test_source="/root/reference/openmmapi/tests/test_ANN_package.cpp"):
+    """..._for_alanine_dipeptide, test_ANN_package.cpp:343-420: 7 backbone atoms, four dihedrals -> 8-15-2 Tanh/Tanh with
+    TRAINED weights.  The 167 trained numbers are read from the reference's test source (build container only; the golden
+    fixture generated from this case carries them to the GPU box), everything else is restated here."""
+    import re
+    text = open(reference_test_source).read()
+    body = text[text.index("for_alanine_dipeptide() {"):]
+    body = body[:body.index("system.addForce")]
+    braces = re.findall(r"\{([-+0-9.eE,\s]+)\}", body)
+    lists = [[float(v) for v in b.replace("\n", " ").split(",") if v.strip()] for b in braces]
+    by_len = {len(v): v for v in lists}
+    f = ANN_Force()
+    f.set_num_of_nodes([8, 15, 2])
+    f.set_layer_types(["Tanh", "Tanh"])
+    f.set_coeffients_of_connections([by_len[120], by_len[30]])
+    f.set_force_constant(10)
+    f.set_potential_center([0.6, 0.5])
+    f.set_values_of_biased_nodes([by_len[15], [v for v in lists if len(v) == 2 and v != [0.6, 0.5]][0]])
+    f.set_list_of_index_of_atoms_forming_dihedrals([[1, 2, 3, 4], [2, 3, 4, 5], [3, 4, 5, 6], [4, 5, 6, 7]])
+    pos = np.array([[-1, -2, -3], [0, 0, 0], [1.5, 0, 0], [0, 0.57, 1], [0.5, 0, 0.1], [0, 0.3, 0.6], [0, 0.4, 0.5]], dtype=np.float64)
+    return f, pos
+
+
 def _glibc():
     return ctypes.CDLL("libc.so.6")
 

@@ -239,6 +239,18 @@ static void test_errors() {
     bool threw = false;
     try { Context context(system, integrator, Platform::getPlatformByName("CUDA")); } catch (const OpenMMException& e) { threw = true; }
     ASSERT(threw);
+    {
+        // a selected atom listed twice is rejected (the reference would sum its two contributions, ANN_ReferenceKernels.cpp:401)
+        System s3;
+        for (int i = 0; i < 4; i++) s3.addParticle(1.0);
+        VerletIntegrator i3(0.01);
+        ANN_Force* g = cartesian_12_4_4("Tanh");
+        g->set_index_of_backbone_atoms({1, 2, 2, 4});
+        s3.addForce(g);
+        threw = false;
+        try { Context c3(s3, i3, Platform::getPlatformByName("CUDA")); } catch (const OpenMMException& e) { threw = true; }
+        ASSERT(threw);
+    }
     CudaANN_KernelFactory factory;
     threw = false;
     try {
@@ -259,7 +271,7 @@ int main() {
         test_cartesian("Softmax", 1.4608776635136895, "double", false);
         test_cartesian("Linear", 26.790165804903218, "mixed", false);
         test_cartesian("Circular", 16.572144252757681, "double", true);
-        for (int n = 20; n < 200; n += 40) test_larger_system(n, 1);     // the reference sweeps 20..180 step 20 (:689-694)
+        for (int n = 20; n < 200; n += 20) test_larger_system(n, 1);     // the reference's sweep, 20..180 step 20 (:689-694)
         test_pair_distances();
         test_dihedrals("Tanh", {0, 0, 0, 0}, 0.5707411857967678);
         test_dihedrals("Circular", {0, 0}, 34.049960896473365);

@@ -59,8 +59,13 @@ def main():
     for tag, act, cen in [("tanh", "Tanh", None), ("circ_00", "Circular", [0, 0]), ("circ_2p4_2p3", "Circular", [2.4, 2.3])]:
         f, pos = cases.dihedral_4_4_4(act, cen)
         dump("ref_dihedral_4_4_4_%s" % tag, f, pos)
-    f, pos = cases.size_sweep(20, seed=1)
-    dump("ref_sweep_20atoms", f, pos)
+    # the full size sweep main() runs, 20 .. 180 atoms step 20 (test_ANN_package.cpp:689-694)
+    for n in range(20, 200, 20):
+        f, pos = cases.size_sweep(n, seed=1)
+        dump("ref_sweep_%datoms" % n, f, pos)
+    # alanine dipeptide, 8-15-2 with trained weights (test_ANN_package.cpp:343-420)
+    f, pos = cases.alanine_dipeptide_8_15_2()
+    dump("ref_alanine_dipeptide_8_15_2", f, pos)
     # --- BASELINE.json shapes, synthetic, fp32-rounded positions ---
     for name, R in [("c1", 8), ("c2", 8), ("c4", 4)]:
         cfg = synthetic.CONFIGS[name]

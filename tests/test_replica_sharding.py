@@ -38,7 +38,11 @@ def _worker(rank, world, port, R, out_dir):
         sharder = ReplicaSharder(R)
         energies = torch.arange(R, dtype=torch.float64) * 1.5 + 0.25          # the "truth", same on every rank
         gathered = sharder.gather_energies(sharder.local_slice(energies).clone())
-        np.save(os.path.join(out_dir, "rank%d.npy" % rank), gathered.numpy())
+        first = gathered.numpy().copy()
+        # a second exchange re-uses the pre-allocated buffers and must see the new values
+        gathered = sharder.gather_energies(sharder.local_slice(energies + 1.0).clone())
+        assert np.array_equal(gathered.numpy(), first + 1.0)
+        np.save(os.path.join(out_dir, "rank%d.npy" % rank), first)
     finally:
         dist.destroy_process_group()
 
