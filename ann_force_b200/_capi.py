@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libannforce_b200.so")
+# ANNF_B200_LIB selects a diagnostic build of the same library (e.g. one made with EXTRA=-DANNF_PHASE_CLOCKS); there is still
+# no fallback: whatever this names must exist and export every symbol
+LIB_PATH = os.environ.get("ANNF_B200_LIB") or os.path.join(HERE, "libannforce_b200.so")
 
 LINEAR, TANH, CIRCULAR, SOFTMAX = 0, 1, 2, 3
 LAYER_CODES = {"Linear": LINEAR, "Tanh": TANH, "Circular": CIRCULAR, "Softmax": SOFTMAX}
@@ -59,6 +61,7 @@ SYMBOLS = {
     "annf_eval_batched_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annf_debug_single_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "annf_debug_stream_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "annf_debug_tensor_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "annf_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "annf_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTime), C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
 }

@@ -54,6 +54,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
                                int kind, std::string* why_not);     // kind: 0 = TF32 pairs, 1 = scaled fp16 pairs
 void tensor_plan_destroy(TensorPlan* plan);
 cudaError_t tensor_plan_reserve(TensorPlan* plan, const NetView& net, int R, cudaStream_t stream);
+cudaError_t tensor_phase_clocks(unsigned long long* out192, bool reset);
 cudaError_t tensor_plan_run(TensorPlan* plan, Profiler* prof, const NetView& net, int R,
                             const float* coords, int atoms_per_replica, const float* centers, float* forces,
                             double* energies, cudaStream_t stream, long long* launches, int slot_index);
@@ -729,6 +730,15 @@ annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks32) {
     ANNF_CUDA(cudaDeviceSynchronize());
     if (h->dmma) ANNF_CUDA(read_dmma_phase_clocks(reinterpret_cast<long long*>(clocks32)));
     else ANNF_CUDA(read_stream_phase_clocks(reinterpret_cast<long long*>(clocks32)));
+    return ANNF_OK;
+}
+
+annf_status annf_debug_tensor_phases(annf_handle h, int64_t* clocks192, int32_t reset) {
+    if (!h || (!clocks192 && !reset)) return fail(ANNF_ERR_INVALID, "annf_debug_tensor_phases: NULL argument");
+    ANNF_NEED_PHASE_CLOCKS("annf_debug_tensor_phases");
+    DeviceGuard guard(h->device);
+    ANNF_CUDA(cudaDeviceSynchronize());
+    ANNF_CUDA(tensor_phase_clocks(reinterpret_cast<unsigned long long*>(clocks192), reset != 0));
     return ANNF_OK;
 }
 

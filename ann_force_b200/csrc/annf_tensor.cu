@@ -85,6 +85,7 @@ struct GemmParams {
     const int* out_exp;               // [M] rows of the result (activations / gradients coming out); unused by EPI_FORCE / EPI_STORE
     const int* aux_exp;               // [M] rows of aux
     const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
+    int dbg;                          // diagnostic builds: slot of g_tensor_clock this launch records into (-1: none)
     int chunk;                        // K-blocks accumulated in TMEM between two promotions into the fp32 register accumulators
     int dry;                          // experiments (ANNF_TENSOR_DRY=1): return immediately, to measure the launch floor
 };
@@ -187,6 +188,22 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kDataBytes = kStageBytes * kStages > kStagingBytes ? kStageBytes * kStages : kStagingBytes;
     static constexpr int kSmemBytes = kDataBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
+
+// Diagnostic build only (make EXTRA=-DANNF_PHASE_CLOCKS): %globaltimer (ns) at the phase boundaries of CTA (0,0,0) of every
+// kernel of the step, plus first / last CTA start and last CTA end over the whole grid.  annf_debug_tensor_phases reads it.
+//   [slot][0..15] phases of CTA 0, [16] min start, [17] max start, [18] max end, over all CTAs
+__device__ unsigned long long g_tensor_clock[8][24];
+#ifdef ANNF_PHASE_CLOCKS
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ANNF_TMARK(slot, i) do { if ((slot) >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tensor_clock[slot][i] = gtimer(); } while (0)
+#define ANNF_TGRID_START(slot) do { if ((slot) >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtimer(); \
+        atomicMin(&g_tensor_clock[slot][16], t_); atomicMax(&g_tensor_clock[slot][17], t_); } } while (0)
+#define ANNF_TGRID_END(slot) do { if ((slot) >= 0 && threadIdx.x == 0) atomicMax(&g_tensor_clock[slot][18], gtimer()); } while (0)
+#else
+#define ANNF_TMARK(slot, i) do { } while (0)
+#define ANNF_TGRID_START(slot) do { } while (0)
+#define ANNF_TGRID_END(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -446,6 +463,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const int kChunk = p.chunk;
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
 
+    ANNF_TGRID_START(p.dbg);
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 0);
     pdl_launch_dependents();                                // the next kernel may start its own prologue now
     if (p.dry & 1) return;
     if (warp == kEpiWarps && lane == 0) {
@@ -474,7 +493,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 1);
     pdl_wait();                                             // everything below reads what earlier kernels wrote
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 2);
 
     if (warp >= kEpiWarps) {
         // ===== producer / MMA warpgroup: needs few registers =====
@@ -495,6 +516,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     }
                     const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
                     const int kc = (kb0 + i) * BK;
+                    if (i == 0) ANNF_TMARK(p.dbg, 3);
                     if (CG == 2) {
                         const uint32_t full_leader = map_to_cta(full, leader_cta);
                         if (pair_rank == 0) mbar_expect_tx(full, (uint32_t) (2 * Cfg::kStageBytes));   // both CTAs' bytes land here
@@ -548,6 +570,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         const uint32_t ph = (uint32_t) (i / kStages) & 1u;
                         mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed (both CTAs)
                         tcgen05_fence_after();
+                        if (i == 0) ANNF_TMARK(p.dbg, 4);
                         const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
                         const uint32_t a_hi = base, a_lo = base + BM * kBlockBytes;
                         const uint32_t b_hi = base + 2 * BM * kBlockBytes, b_lo = b_hi + kBRows * kBlockBytes;
@@ -575,6 +598,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     if (CG == 2) umma_commit_pair(smem_u32(&bar_acc_full[buf]), pair_mask);   // chunk complete, both CTAs' epilogues
                     else umma_commit(smem_u32(&bar_acc_full[buf]));
                 }
+                ANNF_TMARK(p.dbg, 5);
             }
         }
         role_sync<(S > 1 || NX == 2)>();                    // NX = 2: the peer may still multicast into this CTA's stages
@@ -613,6 +637,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
             }
         }
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 6);
         {
             // park the tile in shared memory (all TMA loads have landed and been consumed: the stage buffers are free).
             // Unsplit GEMMs do this too: the epilogue below then walks ROWS with consecutive lanes, i.e. 512-byte coalesced
@@ -624,8 +649,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
         role_sync<(S > 1 || NX == 2)>();                                           // every partial tile (of the split) is parked
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 7);
         if (!(p.dry & 8)) cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
         role_sync<(S > 1 || CX == 2)>();                                           // nobody leaves while peers still read / share TMEM
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
     }
 
     if (warp == kEpiWarps + 1) {
@@ -633,6 +661,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
     }
+    ANNF_TGRID_END(p.dbg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -662,10 +691,13 @@ __device__ __forceinline__ int exp_for_bound(float bound) {
 template <int KIND>
 __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
                                                   void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
-                                                  ExpChain chain) {
+                                                  ExpChain chain, int dbg) {
     extern __shared__ float xs[];                           // [3 * A]
+    ANNF_TGRID_START(dbg);
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
     if (contiguous & 2) return;                             // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = net.n_sel, n0 = 3 * A;
@@ -727,6 +759,7 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
             *reinterpret_cast<float4*>(oh + 4 * v) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4*>(ol + 4 * v) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
+        ANNF_TGRID_END(dbg);
         return;
     }
     // KIND_F16: the features, then the row's largest magnitude -> its scale exponent, then the scaled pair
@@ -771,6 +804,8 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
         *reinterpret_cast<uint2*>(oh + 4 * v) = hi;
         *reinterpret_cast<uint2*>(ol + 4 * v) = lo;
     }
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
+    ANNF_TGRID_END(dbg);
 }
 
 // activation m of a row stored as an operand pair: hi + lo is exact in fp32, and so is the power-of-two unscale
@@ -794,10 +829,13 @@ template <int KIND>
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, const float* __restrict__ centers,
                                                            const void* __restrict__ a_hi, const void* __restrict__ a_lo, int ld,
                                                            void* __restrict__ d_hi, void* __restrict__ d_lo, double* __restrict__ energies,
-                                                           ExpChain chain) {
+                                                           ExpChain chain, int dbg) {
     typedef typename KindOf<KIND>::elem elem;
+    ANNF_TGRID_START(dbg);
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
     if (R < 0) return;                                      // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r_index = r;
@@ -907,6 +945,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
             }
         }
     }
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
+    ANNF_TGRID_END(dbg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -979,6 +1019,7 @@ struct TensorPlan {
     int force_bn = 0;                               // ANNF_GEMM_BN=128|256 (1-CTA tiles) or 512 (CTA pairs) overrides the tile heuristic
     int force_split = 0;                            // ANNF_GEMM_SPLIT_SHORTK=1|2|4|8 overrides split-K for GEMMs with K <= 1024
     int dry = 0;                                    // ANNF_TENSOR_DRY=1: every kernel returns at once (launch-floor measurement)
+    int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
 };
@@ -1286,6 +1327,7 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
     p.M = R;
     p.dry = t->dry;
     p.chunk = t->chunk;
+    p.dbg = t->dbg_next < 8 ? t->dbg_next++ : -1;
     if (p.epi == EPI_FORCE) {
         p.out_hi = forces;
         p.ld_out = 3 * atoms_per_replica;
@@ -1390,11 +1432,12 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
     };
     ExpChain chain = t->chain;
     for (int l = 0; l < kMaxLayers; l++) { chain.x_exp[l] = sl->x_exp[l]; chain.d_exp[l] = sl->d_exp[l]; }
+    t->dbg_next = 0;
     cudaError_t err = timed("prep_kernel", [&] {
         const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
                                (t->dry ? 2 : 0);
         return launch_pdl(prep_kernel<KIND>, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
-                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain);
+                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain, t->dbg_next++);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : sl->fwd) {
@@ -1404,7 +1447,7 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
     }
     err = timed("head_kernel", [&] {
         return launch_pdl(head_kernel<KIND>, dim3(R), dim3(kHeadThreads), 0, stream, 1, 0, net, t->dry ? -R : R, centers, (const void*) sl->x_hi[L - 2],
-                          (const void*) sl->x_lo[L - 2], t->ld[L - 2], sl->d_hi[L - 2], sl->d_lo[L - 2], energies, chain);
+                          (const void*) sl->x_lo[L - 2], t->ld[L - 2], sl->d_hi[L - 2], sl->d_lo[L - 2], energies, chain, t->dbg_next < 8 ? t->dbg_next++ : -1);
     });
     if (err != cudaSuccess) return err;
     for (const GemmOp& op : sl->bwd) {
@@ -1424,6 +1467,16 @@ cudaError_t tensor_plan_run(TensorPlan* t, Profiler* prof, const NetView& net, i
     if (t->kind == KIND_F16)
         return plan_run_t<KIND_F16>(t, prof, net, R, coords, atoms_per_replica, centers, forces, energies, stream, launches, sl);
     return plan_run_t<KIND_TF32>(t, prof, net, R, coords, atoms_per_replica, centers, forces, energies, stream, launches, sl);
+}
+
+// Diagnostic (ANNF_PHASE_CLOCKS builds): resets, or reads, the 8 x 24 %globaltimer marks of the kernels of the last step.
+cudaError_t tensor_phase_clocks(unsigned long long* out192, bool reset) {
+    if (reset) {
+        std::vector<unsigned long long> init(8 * 24, 0ull);
+        for (int s = 0; s < 8; s++) init[s * 24 + 16] = ~0ull;
+        return cudaMemcpyToSymbol(g_tensor_clock, init.data(), sizeof(unsigned long long) * 8 * 24);
+    }
+    return cudaMemcpyFromSymbol(out192, g_tensor_clock, sizeof(unsigned long long) * 8 * 24);
 }
 
 }  // namespace annf

@@ -182,6 +182,12 @@ ANNF_API annf_status annf_debug_single_phases(annf_handle h, int64_t* clocks16);
  * 64 values.  Synchronises. */
 ANNF_API annf_status annf_debug_stream_phases(annf_handle h, int64_t* clocks64);
 
+/* Diagnostic: the tensor-core path (batched_path 1).  8 kernels x 24 values of %globaltimer (ns) from the most recent
+ * annf_eval_batched: [k][0..9] phase boundaries of CTA 0 of kernel k of the step (entry, prologue done, dependencies
+ * resolved, first TMA, first operands landed, last MMA issued, accumulators drained, partials parked, epilogue done, exit),
+ * [k][16] / [k][17] first / last CTA start, [k][18] last CTA end.  reset != 0 clears the marks instead.  Synchronises. */
+ANNF_API annf_status annf_debug_tensor_phases(annf_handle h, int64_t* clocks192, int32_t reset);
+
 /* Per-kernel device timing with CUDA events on the launching stream (for the roofline line). */
 ANNF_API annf_status annf_set_profiling(annf_handle h, int32_t enabled);
 ANNF_API annf_status annf_get_kernel_times(annf_handle h, annf_kernel_time* out, int32_t capacity, int32_t* count, int32_t reset);
