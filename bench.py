@@ -414,6 +414,16 @@ def main():
                     empty_kernel_us_per_step_stream=leg.get("empty_kernel_us_per_step_stream"),
                     empty_kernel_us_per_step_graph=leg.get("empty_kernel_us_per_step_graph"),
                     note="both are bound by kernel launch + a chain of dependent layers; ours runs fp64, the legacy scheme fp32")
+                # the legacy plugin's other input mode: the same network on the 21 pair distances of the 7 atoms
+                leg = json.loads(subprocess.run([legacy, "20000", "pairs"], check=True, capture_output=True, text=True, timeout=120).stdout)
+                ours = json.loads(subprocess.run([exe, "20000", "c1pairs"], check=True, capture_output=True, text=True, timeout=120).stdout)
+                e2e["vs_legacy_restatement_c1_pair_distances"] = dict(
+                    what=leg["what"], network=leg["network"],
+                    legacy_us_per_step_stream=leg["us_per_step_stream"], legacy_us_per_step_graph=leg["us_per_step_graph"],
+                    ours_us_per_step_stream=ours["gpu_us_per_step"], ours_us_per_step_graph=ours["graph_us_per_step"],
+                    speedup_stream=leg["us_per_step_stream"] / ours["gpu_us_per_step"],
+                    speedup_graph=leg["us_per_step_graph"] / ours["graph_us_per_step"],
+                    note="pair-distance input runs on the generic single-replica kernel (fp64)")
         except Exception as exc:       # noqa: BLE001
             e2e["legacy_error"] = str(exc)[:200]
 

@@ -1,8 +1,9 @@
 // Per-step cost of the bias force THROUGH THE C++ PLUGIN LAYER (ANN_ForceImpl::calcForcesAndEnergy ->
 // CudaCalcANN_ForceKernel::execute -> annf_eval_openmm), i.e. what OpenMM pays per MD step.  BASELINE config 2:
 // alanine dipeptide, 22 atoms, 7 backbone heavy atoms selected, 21-40-4 Tanh/Circular, mixed precision.
-// Prints one JSON object.  usage: bench_plugin [steps] [c2|c1]     (c1 = 21-40-2 Tanh/Tanh, the shape the legacy CUDA
-// plugin supports: compare with tools/legacy_restatement)
+// Prints one JSON object.  usage: bench_plugin [steps] [c2|c1|c1pairs]     (c1 = 21-40-2 Tanh/Tanh, the shape the legacy CUDA
+// plugin supports; c1pairs = the same network fed with the 21 pair distances of the 7 atoms, the legacy plugin's other input
+// mode: compare with tools/legacy_restatement [steps] [pairs])
 #include "OpenMM.h"
 #include "OpenMM_ANN.h"
 #include "CudaANN_KernelFactory.h"
@@ -22,7 +23,8 @@ static double lcg(unsigned long long& s) { s = s * 6364136223846793005ULL + 1442
 
 int main(int argc, char** argv) {
     const int steps = argc > 1 ? atoi(argv[1]) : 20000;
-    const bool c1 = argc > 2 && string(argv[2]) == "c1";
+    const bool pairs = argc > 2 && string(argv[2]) == "c1pairs";
+    const bool c1 = pairs || (argc > 2 && string(argv[2]) == "c1");
     registerANN_CudaKernelFactories();
     System system;
     const int num_atoms = 22;
@@ -43,8 +45,15 @@ int main(int argc, char** argv) {
     f->set_potential_center(c1 ? vector<double>({0.3, 0.3}) : vector<double>({0.7, -1.1}));
     f->set_force_constant(500);
     f->set_scaling_factor(0.5);
-    f->set_index_of_backbone_atoms({2, 5, 7, 9, 15, 17, 19});     // ACE-ALA-NME backbone heavy atoms
-    f->set_data_type_in_input_layer(1);
+    const vector<int> backbone = {2, 5, 7, 9, 15, 17, 19};         // ACE-ALA-NME backbone heavy atoms
+    f->set_index_of_backbone_atoms(backbone);
+    f->set_data_type_in_input_layer(pairs ? 2 : 1);
+    if (pairs) {
+        vector<vector<int> > list;
+        for (size_t i = 0; i < backbone.size(); i++)
+            for (size_t j = i + 1; j < backbone.size(); j++) list.push_back({backbone[i], backbone[j]});   // 7 choose 2 = 21 inputs
+        f->set_list_of_pair_index_for_distances(list);
+    }
     system.addForce(f);
     VerletIntegrator integrator(0.002);
     map<string, string> props; props["Precision"] = "mixed";
@@ -86,7 +95,7 @@ int main(int argc, char** argv) {
     }
     printf("{\"network\": \"%s\", \"steps\": %d, \"gpu_us_per_step\": %.4f, \"wall_us_per_step\": %.4f, \"graph_us_per_step\": %.4f, "
            "\"energy\": %.12g, \"path\": \"ANN_ForceImpl::calcForcesAndEnergy -> CudaCalcANN_ForceKernel::execute -> annf_eval_openmm\"}\n",
-           c1 ? "21-40-2 Tanh/Tanh" : "21-40-4 Tanh/Circular", steps, 1e3 * ms / steps, wall_us,
+           pairs ? "21-40-2 Tanh/Tanh, 21 pair distances" : (c1 ? "21-40-2 Tanh/Tanh" : "21-40-4 Tanh/Circular"), steps, 1e3 * ms / steps, wall_us,
            ms_graph < 0 ? -1.0 : 1e3 * ms_graph / (steps / 100 * 100), e_check);
     return 0;
 }

@@ -10,7 +10,9 @@
 //   * thread 0 alone forms the forces (:326-337); every thread then adds its (mostly zero) forces and energy to the
 //     context buffers, as OpenMM's bonded kernel does for each "bond" [OpenMM API knowledge].
 // It is favourable to the legacy scheme: no other bonded terms share the launch, and one 128-thread block is launched.
-// usage: legacy_restatement [steps]   -> one JSON object
+// `pairs` selects the legacy plugin's other input mode, pair distances (:210-256 features, :339-351 forces): the same 21-40-2
+// network fed with the 21 distances between the 7 atoms; every thread computes every distance, thread 0 forms the forces.
+// usage: legacy_restatement [steps] [pairs]   -> one JSON object
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
@@ -29,7 +31,9 @@ struct LegacyArgs {
     float *in0, *in1, *in2;            // global scratch "INPUT_0..2"
     float k, scale;
     int atom[kAtoms];
+    int pairs;                         // 0: Cartesian input, 1: pair distances
 };
+constexpr int kPairs = kAtoms * (kAtoms - 1) / 2;          // 21 = kN0
 
 __global__ void legacy_style_kernel(LegacyArgs a) {
     const int index = blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,7 +41,18 @@ __global__ void legacy_style_kernel(LegacyArgs a) {
     float energy = 0.f;
     float3 f[kAtoms];
     for (int i = 0; i < kAtoms; i++) f[i] = make_float3(0.f, 0.f, 0.f);
-    if (bond) {
+    float3 delta[kPairs];
+    float dis[kPairs];
+    if (bond && a.pairs) {
+        int t = 0;
+        for (int i = 0; i < kAtoms; i++)                         // every thread computes every distance (:239-256)
+            for (int j = i + 1; j < kAtoms; j++, t++) {
+                const float4 p = a.posq[a.atom[i]], q = a.posq[a.atom[j]];
+                delta[t] = make_float3(p.x - q.x, p.y - q.y, p.z - q.z);
+                dis[t] = sqrtf(delta[t].x * delta[t].x + delta[t].y * delta[t].y + delta[t].z * delta[t].z) / a.scale;
+                a.in0[t] = dis[t];
+            }
+    } else if (bond) {
         for (int i = 0; i < kAtoms; i++) {                       // every thread writes every input (:189-193)
             const float4 p = a.posq[a.atom[i]];
             a.in0[3 * i] = p.x / a.scale; a.in0[3 * i + 1] = p.y / a.scale; a.in0[3 * i + 2] = p.z / a.scale;
@@ -86,7 +101,23 @@ __global__ void legacy_style_kernel(LegacyArgs a) {
             a.in0[i] = t;
         }
     __syncthreads();
-    if (bond) {
+    if (bond && a.pairs) {
+        if (index == 0) {                                        // thread 0 alone forms the forces (:343-350)
+            int t = 0;
+            for (int i = 0; i < kAtoms; i++)
+                for (int j = i + 1; j < kAtoms; j++, t++) {
+                    const float c = a.in0[t] / (a.scale * a.scale * dis[t]);
+                    f[i].x -= delta[t].x * c; f[i].y -= delta[t].y * c; f[i].z -= delta[t].z * c;
+                    f[j].x += delta[t].x * c; f[j].y += delta[t].y * c; f[j].z += delta[t].z * c;
+                }
+        }
+        for (int i = 0; i < kAtoms; i++) {
+            atomicAdd(&a.force[a.atom[i]], (unsigned long long) ((long long) (f[i].x * 0x100000000)));
+            atomicAdd(&a.force[a.atom[i] + a.padded], (unsigned long long) ((long long) (f[i].y * 0x100000000)));
+            atomicAdd(&a.force[a.atom[i] + 2 * a.padded], (unsigned long long) ((long long) (f[i].z * 0x100000000)));
+        }
+        a.energy[index] += energy;
+    } else if (bond) {
         float3 avg = make_float3(0.f, 0.f, 0.f);                 // every thread averages (:313-320) ...
         for (int i = 0; i < kAtoms; i++) { avg.x += a.in0[3 * i]; avg.y += a.in0[3 * i + 1]; avg.z += a.in0[3 * i + 2]; }
         avg.x /= kAtoms; avg.y /= kAtoms; avg.z /= kAtoms;
@@ -116,6 +147,7 @@ template <typename T> static T* upload(const std::vector<T>& v) {
 
 int main(int argc, char** argv) {
     const int steps = argc > 1 ? atoi(argv[1]) : 20000;
+    const bool pairs = argc > 2 && argv[2][0] == 'p';
     unsigned long long seed = 1234;
     std::vector<float> c0(kN1 * kN0), c1(kN2 * kN1), b0(kN1), b1(kN2), cen = {0.3f, 0.3f};
     const double bound0 = sqrt(6.0 / (kN0 + kN1)), bound1 = sqrt(6.0 / (kN1 + kN2));
@@ -136,6 +168,7 @@ int main(int argc, char** argv) {
     a.coeff0 = upload(c0); a.coeff1 = upload(c1); a.bias0 = upload(b0); a.bias1 = upload(b1); a.center = upload(cen);
     cudaMalloc((void**) &a.in0, sizeof(float) * kN0); cudaMalloc((void**) &a.in1, sizeof(float) * kN1); cudaMalloc((void**) &a.in2, sizeof(float) * kN2);
     a.k = 500.f; a.scale = 0.5f;
+    a.pairs = pairs ? 1 : 0;
     const int sel[kAtoms] = {1, 4, 6, 8, 14, 16, 18};
     for (int i = 0; i < kAtoms; i++) a.atom[i] = sel[i];
     cudaStream_t stream;
@@ -187,10 +220,10 @@ int main(int argc, char** argv) {
     float ms_empty_graph = 0.f;
     cudaEventElapsedTime(&ms_empty_graph, e0, e1);
     const cudaError_t err = cudaGetLastError();
-    printf("{\"what\": \"restatement of the legacy plugin's generated kernel (NOT the legacy plugin)\", \"network\": \"21-40-2 Tanh/Tanh, 7 of 22 atoms, fp32\", "
+    printf("{\"what\": \"restatement of the legacy plugin's generated kernel (NOT the legacy plugin)\", \"network\": \"21-40-2 Tanh/Tanh, 7 of 22 atoms, %s, fp32\", "
            "\"steps\": %d, \"us_per_step_stream\": %.4f, \"us_per_step_graph\": %.4f, \"empty_kernel_us_per_step_stream\": %.4f, "
            "\"empty_kernel_us_per_step_graph\": %.4f, \"cuda_error\": \"%s\"}\n",
-           steps, 1e3 * ms / steps, 1e3 * ms_graph / (steps / 100 * 100), 1e3 * ms_empty / steps, 1e3 * ms_empty_graph / (steps / 100 * 100),
+           pairs ? "21 pair distances" : "Cartesian input", steps, 1e3 * ms / steps, 1e3 * ms_graph / (steps / 100 * 100), 1e3 * ms_empty / steps, 1e3 * ms_empty_graph / (steps / 100 * 100),
            cudaGetErrorString(err));
     return err == cudaSuccess ? 0 : 1;
 }
