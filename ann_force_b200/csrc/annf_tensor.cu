@@ -85,6 +85,7 @@ struct GemmParams {
     const int* out_exp;               // [M] rows of the result (activations / gradients coming out); unused by EPI_FORCE / EPI_STORE
     const int* aux_exp;               // [M] rows of aux
     const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
+    int direct_store;                 // EPI_FORCE, unsplit, identity selection, 16-byte aligned rows: the tile leaves through tm_out (TMA store)
     int dbg;                          // diagnostic builds: slot of g_tensor_clock this launch records into (-1: none)
     int chunk;                        // K-blocks accumulated in TMEM between two promotions into the fp32 register accumulators
     int dry;                          // experiments (ANNF_TENSOR_DRY=1): return immediately, to measure the launch floor
@@ -117,6 +118,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// shared -> global tile store by the TMA engine (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -186,7 +197,19 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kStagingLd = BN + 4;                                   // fp32 elements, padded against bank conflicts
     static constexpr int kStagingBytes = BM * kStagingLd * 4;
     static constexpr int kDataBytes = kStageBytes * kStages > kStagingBytes ? kStageBytes * kStages : kStagingBytes;
-    static constexpr int kSmemBytes = kDataBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kAccBufs = 512 / BN;                                   // TMEM accumulator buffers (all 512 columns are used)
+    static constexpr int kVecBytes = (2 * BN + 3 * BM) * 4;                     // per-tile epilogue vectors: b_exp, bias | a_exp, out_exp, aux_exp
+    static constexpr int kSmemBytes = kDataBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kVecBytes;
+};
+
+// Per-tile epilogue operands staged in shared memory by an otherwise idle warp while the main loop runs, so that the
+// epilogue itself issues no global loads (each one was a full L2 round trip on the critical path of a short kernel).
+struct EpiVec {
+    const int* b_exp;                 // [BN] scale exponents of the tile's B rows = output columns   (KIND_F16)
+    const float* bias;                // [BN]                                                          (EPI_BIAS_*)
+    const int* a_exp;                 // [BM] scale exponents of the tile's A rows                      (KIND_F16)
+    const int* out_exp;               // [BM] scale exponents of the rows coming out                    (KIND_F16)
+    const int* aux_exp;               // [BM] scale exponents of the aux rows                           (KIND_F16, EPI_TANH_GRAD)
 };
 
 // Diagnostic build only (make EXTRA=-DANNF_PHASE_CLOCKS): %globaltimer (ns) at the phase boundaries of CTA (0,0,0) of every
@@ -287,25 +310,26 @@ __device__ __forceinline__ void split_f16x4(float4 v, uint2& hi, uint2& lo) {
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
+// (m, n) global row / first column of the group; (lr, lc) the same inside the tile (indices into the staged vectors)
 template <int KIND>
-__device__ __forceinline__ EpiAux epilogue_load(const GemmParams& p, int m, int n) {
+__device__ __forceinline__ EpiAux epilogue_load(const GemmParams& p, const EpiVec& vec, int m, int n, int lr, int lc) {
     EpiAux x;
     x.a = make_float4(0.f, 0.f, 0.f, 0.f);
     x.b = x.a;
     x.unscale = make_float4(1.f, 1.f, 1.f, 1.f);
     x.out_scale = 1.f;
     if (KIND == KIND_F16) {
-        const int ea = __ldg(p.a_exp + m);
-        const int4 eb = __ldg(reinterpret_cast<const int4*>(p.b_exp + n));
+        const int ea = vec.a_exp[lr];
+        const int4 eb = *reinterpret_cast<const int4*>(vec.b_exp + lc);
         x.unscale = make_float4(exp2i(-(ea + eb.x)), exp2i(-(ea + eb.y)), exp2i(-(ea + eb.z)), exp2i(-(ea + eb.w)));
-        if (p.epi != EPI_STORE && p.epi != EPI_FORCE) x.out_scale = exp2i(__ldg(p.out_exp + m));
+        if (p.epi != EPI_STORE && p.epi != EPI_FORCE) x.out_scale = exp2i(vec.out_exp[lr]);
     }
     if (p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) {
-        x.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        x.a = *reinterpret_cast<const float4*>(vec.bias + lc);
     } else if (p.epi == EPI_TANH_GRAD) {
         if (KIND == KIND_F16) {
             // a = (hi + lo) * 2^-e: the sum of the pair is exact in fp32 and so is the power-of-two unscale
-            const float un = exp2i(-__ldg(p.aux_exp + m));
+            const float un = exp2i(-vec.aux_exp[lr]);
             const float4 h = half4_to_float4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.aux_hi) + (size_t) m * p.ld_aux + n)));
             const float4 l = half4_to_float4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.aux_lo) + (size_t) m * p.ld_aux + n)));
             x.a = make_float4((h.x + l.x) * un, (h.y + l.y) * un, (h.z + l.z) * un, (h.w + l.w) * un);
@@ -364,9 +388,11 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
 
 // Cooperative epilogue over the parked tile(s): thread t of kGroupThreads walks (row, 4-column) groups with consecutive lanes
 // along a row — 512-byte coalesced global accesses — summing the S split-K partials (own + peers', through DSMEM) in a fixed
-// order, with the auxiliary global loads of four groups issued ahead of the dependent math.
+// order.  The loop is ROLLED and software-pipelined by hand (the loads of group g + 1 are issued before the math of group g):
+// this code runs a handful of times per CTA, so its size is paid in instruction-cache misses — ~170 cycles per 128-byte
+// line of cold code — and an unrolled body with 16 inlined tanhf was most of the 4-6 us this epilogue used to take.
 template <int KIND, int BN, int S, int CG, int kGroupThreads, int CX = CG>
-__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
+__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const EpiVec& vec, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int kRows = (BM + S - 1) / S;                                        // rows this CTA finishes (S = 3: 43, 43, 42)
     constexpr int kVecPerRow = BN / 4;
@@ -380,32 +406,30 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, unsign
         peer[0] = staging;
     }
     constexpr int kGroups = (kRows * kVecPerRow + kGroupThreads - 1) / kGroupThreads;   // groups per thread
-    constexpr int kBatch = 4;
-#pragma unroll 1
-    for (int g0 = 0; g0 < kGroups; g0 += kBatch) {
-        EpiAux aux[kBatch];
-        float4 sum[kBatch];
-        int mm[kBatch], nn[kBatch];
-        bool ok[kBatch];
+    struct Group { EpiAux aux; float4 sum; int m, n; bool ok; };
+    auto fetch = [&](int g) {
+        Group q;
+        const int v = t + g * kGroupThreads;
+        const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
+        q.m = m0 + row; q.n = n0 + col;
+        q.ok = g < kGroups && v < kRows * kVecPerRow && row < BM && q.m < p.M && q.n < p.N;
+        q.sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q.ok) {
+            q.aux = epilogue_load<KIND>(p, vec, q.m, q.n, row, col);
 #pragma unroll
-        for (int u = 0; u < kBatch; u++) {                                         // all the loads of the batch first
-            const int v = t + (g0 + u) * kGroupThreads;
-            const int row = rank * kRows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
-            mm[u] = m0 + row; nn[u] = n0 + col;
-            ok[u] = (g0 + u) < kGroups && v < kRows * kVecPerRow && row < BM && mm[u] < p.M && nn[u] < p.N;
-            sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[u]) {
-                aux[u] = epilogue_load<KIND>(p, mm[u], nn[u]);
-#pragma unroll
-                for (int r = 0; r < S; r++) {                                      // fixed order: deterministic
-                    const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
-                    sum[u].x += x.x; sum[u].y += x.y; sum[u].z += x.z; sum[u].w += x.w;
-                }
+            for (int r = 0; r < S; r++) {                                          // fixed order: deterministic
+                const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
+                q.sum.x += x.x; q.sum.y += x.y; q.sum.z += x.z; q.sum.w += x.w;
             }
         }
-#pragma unroll
-        for (int u = 0; u < kBatch; u++)
-            if (ok[u]) epilogue_finish<KIND>(p, mm[u], nn[u], sum[u], aux[u]);
+        return q;
+    };
+    Group next = fetch(0);
+#pragma unroll 1
+    for (int g = 0; g < kGroups; g++) {
+        const Group cur = next;
+        next = fetch(g + 1);
+        if (cur.ok) epilogue_finish<KIND>(p, cur.m, cur.n, cur.sum, cur.aux);
     }
 }
 
@@ -425,7 +449,8 @@ template <bool kCluster> __device__ __forceinline__ void role_sync() {
 template <int KIND, int BN, int S, int CG, int NX = 1>
 __global__ void __launch_bounds__(GemmCfg<BN, CG>::kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-              const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmParams p) {
+              const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+              const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int BK = KindOf<KIND>::kBlockElems;           // operand values per K-block (one 128-byte swizzle span)
     constexpr int kStages = Cfg::kStages;
@@ -437,13 +462,22 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms (TMA and UMMA must agree on address bits 7..9)
     unsigned char* data = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]   (CG = 2: full and acc_empty are used in the leader only)
+    // barriers: full[kStages], empty[kStages], acc_full[NB], acc_empty[NB]   (CG = 2: full and acc_empty are used in the leader only)
+    constexpr int NB = Cfg::kAccBufs;                       // TMEM accumulator buffers: 4 (BN = 128) or 2 (BN = 256)
     uint64_t* bars = reinterpret_cast<uint64_t*>(data + Cfg::kDataBytes);
     uint64_t* bar_full = bars;
     uint64_t* bar_empty = bars + kStages;
     uint64_t* bar_acc_full = bars + 2 * kStages;
-    uint64_t* bar_acc_empty = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* bar_acc_empty = bars + 2 * kStages + NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * NB);
+    static_assert((2 * 4 + 2 * 4) * 8 + 4 <= 256, "barrier region");
+    // per-tile epilogue vectors (EpiVec), staged by warp kEpiWarps + 2
+    int* s_b_exp = reinterpret_cast<int*>(data + Cfg::kDataBytes + 256);
+    float* s_bias = reinterpret_cast<float*>(s_b_exp + BN);
+    int* s_a_exp = reinterpret_cast<int*>(s_bias + BN);
+    int* s_out_exp = s_a_exp + BM;
+    int* s_aux_exp = s_out_exp + BM;
+    const EpiVec vec = {s_b_exp, s_bias, s_a_exp, s_out_exp, s_aux_exp};
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     static_assert(NX == 1 || (CG == 1 && NX == 2), "operand multicast is implemented for pairs of 1-CTA tiles");
@@ -462,6 +496,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const int num_kb = kb1 - kb0;
     const int kChunk = p.chunk;
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
+    const bool direct = p.direct_store != 0;                // unsplit force GEMM: registers -> swizzled tile -> TMA store
 
     ANNF_TGRID_START(p.dbg);
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 0);
@@ -473,7 +508,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             mbar_init(smem_u32(&bar_full[s]), CG);                  // leader's arrive.expect_tx (+ the peer's remote arrive)
             mbar_init(smem_u32(&bar_empty[s]), NX);                 // NX = 2: both CTAs' MMA commits
         }
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NB; b++) {
             mbar_init(smem_u32(&bar_acc_full[b]), 1);
             mbar_init(smem_u32(&bar_acc_empty[b]), CG * kEpiWarps);   // one arrival per epilogue warp (of both CTAs)
         }
@@ -481,11 +516,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     }
     if (warp == kEpiWarps + 1) {
         if (CG == 2) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (NB * BN)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (2 * BN)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (NB * BN)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    if (warp == kEpiWarps + 2) {
+        // static per-tile vectors (weights' scale exponents, biases): not produced by an earlier kernel of the step
+        for (int c = lane; c < BN; c += 32) {
+            const int n = n0 + c;
+            s_b_exp[c] = (KIND == KIND_F16 && n < p.N) ? __ldg(p.b_exp + n) : 0;
+            s_bias[c] = ((p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) && n < p.N) ? __ldg(p.bias + n) : 0.f;
         }
     }
     tcgen05_fence_before();
@@ -496,7 +539,35 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 1);
     pdl_wait();                                             // everything below reads what earlier kernels wrote
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 2);
+    if (warp == kEpiWarps + 2) {
+        // per-row scale exponents written by earlier kernels of the step; published to the epilogue by named barrier 1
+        if (KIND == KIND_F16) {
+            const bool has_out = p.epi != EPI_STORE && p.epi != EPI_FORCE;
+            for (int r = lane; r < BM; r += 32) {
+                const int m = m0 + r;
+                s_a_exp[r] = m < p.M ? p.a_exp[m] : 0;
+                s_out_exp[r] = (has_out && m < p.M) ? p.out_exp[m] : 0;
+                s_aux_exp[r] = (p.epi == EPI_TANH_GRAD && m < p.M) ? p.aux_exp[m] : 0;
+            }
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"n"(32 * (kEpiWarps + 1)) : "memory");
+    }
 
+    // Rendezvous + epilogue, the same for every warp role.  BN = 128: ONE instance after the roles re-join (the epilogue's code is
+    // large: see cooperative_epilogue), and the producer / MMA warps, idle by then and still holding their registers, take a
+    // share of it.  BN = 256: one instance per role, INSIDE the region governed by that role's setmaxnreg (the producer
+    // warpgroup gave its registers away and only keeps the rendezvous; code after the roles re-join could not assume either
+    // register budget).
+    auto finish_tile = [&](bool participates) {
+        role_sync<(S > 1 || NX == 2)>();                    // every partial tile (of the split) is parked; NX = 2: the peer no longer multicasts into this CTA's stages
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 7);
+        if (participates && !(p.dry & 8) && !(S == 1 && direct))
+            cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, data, rank, x_rank, m0, n0, (int) threadIdx.x);
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
+        role_sync<(S > 1 || CX == 2)>();                    // nobody leaves while peers still read / share TMEM
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
+    };
     if (warp >= kEpiWarps) {
         // ===== producer / MMA warpgroup: needs few registers =====
         if (BN >= 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
@@ -558,8 +629,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 const uint16_t pair_mask = (uint16_t) (3u << leader_cta);          // both CTAs of this pair
                 int i = 0;
                 for (int c = 0; c < num_chunks; c++) {
-                    const int buf = c & 1;
-                    const uint32_t use = (uint32_t) (c >> 1);
+                    const int buf = c % NB;
+                    const uint32_t use = (uint32_t) (c / NB);
                     mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);    // epilogue warps (of both CTAs) drained this buffer
                     tcgen05_fence_after();
                     const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * BN);
@@ -601,12 +672,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 ANNF_TMARK(p.dbg, 5);
             }
         }
-        role_sync<(S > 1 || NX == 2)>();                    // NX = 2: the peer may still multicast into this CTA's stages
-        // BN = 128: these warps are idle by now and keep their registers: they take a share of the epilogue.
-        // BN = 256: they gave their registers to the epilogue warps (setmaxnreg) and only keep the rendezvous.
-        if (BN < 256 && !(p.dry & 8))
-            cooperative_epilogue<KIND, BN, S, CG, Cfg::kThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
-        role_sync<(S > 1 || CX == 2)>();
+        if (BN >= 256) finish_tile(false);
     } else {
         // ===== epilogue warps: promote TMEM chunks into fp32 registers (round-to-nearest adds) =====
         if (BN >= 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
@@ -617,8 +683,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
 #pragma unroll
         for (int j = 0; j < kColsPerWarp; j++) acc[j] = 0.f;
         for (int c = 0; c < num_chunks; c++) {
-            const int buf = c & 1;
-            const uint32_t use = (uint32_t) (c >> 1);
+            const int buf = c % NB;
+            const uint32_t use = (uint32_t) (c / NB);
             mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
             tcgen05_fence_after();
 #pragma unroll
@@ -638,7 +704,33 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             }
         }
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 6);
-        {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + 1)) : "memory");    // the staged per-tile vectors are in place
+        if (S == 1 && direct) {
+            // Unsplit force GEMM writing whole rows: every thread turns its own accumulators into forces (x 2^-(e_row + e_col)),
+            // parks them in the layout of a 128-byte-swizzled TMA box (32 columns x 128 rows per box: lane = row, and the
+            // 16-byte unit index is XORed with row % 8, so the 32 lanes of a store hit every bank exactly four times), and ONE
+            // thread hands the boxes to the TMA engine.  The thread-per-group store loop this replaces was latency-bound:
+            // 10.8 us for 18 MB at BASELINE C5 (profiles/r02_c5_phases.md).  Rows >= M and columns >= N are clipped by the TMA unit.
+            const int ea = KIND == KIND_F16 ? s_a_exp[row] : 0;
+            unsigned char* dst = data + (size_t) row * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < kColsPerWarp / 4; j4++) {
+                const int c = col0 + 4 * j4;
+                float4 v = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+                if (KIND == KIND_F16) {
+                    const int4 eb = *reinterpret_cast<const int4*>(s_b_exp + c);
+                    v.x *= exp2i(-(ea + eb.x)); v.y *= exp2i(-(ea + eb.y)); v.z *= exp2i(-(ea + eb.z)); v.w *= exp2i(-(ea + eb.w));
+                }
+                *reinterpret_cast<float4*>(dst + (size_t) (c >> 5) * (BM * 128) + (((j4 & 7) ^ (row & 7)) << 4)) = v;
+            }
+            fence_proxy_async_smem();                                              // generic-proxy writes -> visible to the TMA engine
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            if (threadIdx.x == 0) {
+                for (int cb = 0; cb < BN / 32; cb++)
+                    if (n0 + cb * 32 < p.N) tma_store_2d(&tm_out, smem_u32(data + (size_t) cb * (BM * 128)), n0 + cb * 32, m0);
+                tma_store_commit_and_wait_read();                                  // shared memory has been read: the CTA may leave
+            }
+        } else {
             // park the tile in shared memory (all TMA loads have landed and been consumed: the stage buffers are free).
             // Unsplit GEMMs do this too: the epilogue below then walks ROWS with consecutive lanes, i.e. 512-byte coalesced
             // global stores, instead of every lane writing 16 bytes into a different row (measured: 47 -> 27 us on the
@@ -648,18 +740,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             for (int j = 0; j < kColsPerWarp; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
-        role_sync<(S > 1 || NX == 2)>();                                           // every partial tile (of the split) is parked
-        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 7);
-        if (!(p.dry & 8)) cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, data, rank, x_rank, m0, n0, (int) threadIdx.x);
-        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
-        role_sync<(S > 1 || CX == 2)>();                                           // nobody leaves while peers still read / share TMEM
-        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
+        if (BN >= 256) finish_tile(true);
     }
+    if (BN < 256) finish_tile(true);
 
     if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
-        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (2 * BN)) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (NB * BN)) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (NB * BN)) : "memory");
     }
     ANNF_TGRID_END(p.dbg);
 }
@@ -687,7 +775,12 @@ __device__ __forceinline__ int exp_for_bound(float bound) {
 }
 
 // prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), centroid in fp64, write the operand pair.
-// One CTA per replica; the replica's selected coordinates are staged once in shared memory.
+// One CTA per replica; the replica's selected coordinates are staged once in shared memory.  Two passes and ONE block barrier:
+//   pass 1  global -> shared, per-component fp64 sums and fp32 min / max (the largest |p - centroid| of a component is attained
+//           at its min or max, so the row's scale exponent needs no pass of its own);
+//   pass 2  shared -> (p - centroid) / s in fp64 -> x 2^e -> operand pair -> global.
+// Work is walked in groups of 12 floats = 4 atoms, so that the component of every element is static (n_0 = 3A is a multiple
+// of 4 on this path, hence of 12).
 template <int KIND>
 __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
                                                   void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
@@ -700,109 +793,109 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
     if (contiguous & 2) return;                             // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int A = net.n_sel, n0 = 3 * A;
+    const int A = net.n_sel, quads = A / 4;
     const float* base = coords + (size_t) r * N * 3;
-    __shared__ double red[8][3];
-    __shared__ double com[3];
-    __shared__ float redm[8];
+    __shared__ double red_sum[8][3];
+    __shared__ float red_min[8][3], red_max[8][3];
     double s[3] = {0.0, 0.0, 0.0};
-    if (contiguous & 1) {
-        // selection is atoms 0..A-1 and rows are 16-byte aligned: straight vector copy, component = index % 3
-        const float4* src = reinterpret_cast<const float4*>(base);
-        for (int v = tid; v < n0 / 4; v += 256) {
-            const float4 p = __ldg(src + v);
-            *reinterpret_cast<float4*>(xs + 4 * v) = p;
-            const float e[4] = {p.x, p.y, p.z, p.w};
-            int c = (4 * v) % 3;
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int g = tid; g < quads; g += 256) {
+        float e[12];
+        if (contiguous & 1) {
+            // selection is atoms 0..A-1 and rows are 16-byte aligned: three vector loads per 4 atoms
+            const float4* src = reinterpret_cast<const float4*>(base) + 3 * g;
+            const float4 p0 = __ldg(src), p1 = __ldg(src + 1), p2 = __ldg(src + 2);
+            e[0] = p0.x; e[1] = p0.y; e[2] = p0.z; e[3] = p0.w; e[4] = p1.x; e[5] = p1.y; e[6] = p1.z; e[7] = p1.w;
+            e[8] = p2.x; e[9] = p2.y; e[10] = p2.z; e[11] = p2.w;
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                s[0] += c == 0 ? (double) e[j] : 0.0;
-                s[1] += c == 1 ? (double) e[j] : 0.0;
-                s[2] += c == 2 ? (double) e[j] : 0.0;
-                c = c == 2 ? 0 : c + 1;
+            for (int k = 0; k < 4; k++) {
+                const float* p = base + (size_t) net.sel_atoms[4 * g + k] * 3;
+                e[3 * k] = __ldg(p); e[3 * k + 1] = __ldg(p + 1); e[3 * k + 2] = __ldg(p + 2);
             }
         }
-    } else {
-        for (int i = tid; i < A; i += 256) {
-            const float* p = base + (size_t) net.sel_atoms[i] * 3;
-            const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-            xs[3 * i] = x; xs[3 * i + 1] = y; xs[3 * i + 2] = z;
-            s[0] += (double) x; s[1] += (double) y; s[2] += (double) z;
+        float4* dst = reinterpret_cast<float4*>(xs) + 3 * g;
+        dst[0] = make_float4(e[0], e[1], e[2], e[3]);
+        dst[1] = make_float4(e[4], e[5], e[6], e[7]);
+        dst[2] = make_float4(e[8], e[9], e[10], e[11]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            s[c] += ((double) e[c] + (double) e[3 + c]) + ((double) e[6 + c] + (double) e[9 + c]);
+            mn[c] = fminf(fminf(mn[c], fminf(e[c], e[3 + c])), fminf(e[6 + c], e[9 + c]));
+            mx[c] = fmaxf(fmaxf(mx[c], fmaxf(e[c], e[3 + c])), fmaxf(e[6 + c], e[9 + c]));
         }
     }
-    for (int c = 0; c < 3; c++) s[c] = warp_sum(s[c]);
-    if (lane == 0) { red[warp][0] = s[0]; red[warp][1] = s[1]; red[warp][2] = s[2]; }
-    __syncthreads();
-    if (tid < 3) {
-        double t = 0.0;
-        for (int w = 0; w < 8; w++) t += red[w][tid];
-        com[tid] = t / A;                                    // centroid of the unscaled coordinates
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        s[c] = warp_sum(s[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { red_sum[warp][c] = s[c]; red_min[warp][c] = mn[c]; red_max[warp][c] = mx[c]; }
     }
     __syncthreads();
+    // every thread finishes the reduction itself (72 broadcast reads) instead of a second barrier
     const double inv_scale = 1.0 / net.scale;
-    const double c0 = com[0], c1 = com[1], c2 = com[2];
+    double cc[3];
+    float bound = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double t = 0.0;
+        float lo = 3.0e38f, hi = -3.0e38f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
+        cc[c] = t / A;                                       // centroid of the unscaled coordinates
+        bound = fmaxf(bound, (float) (fmax(fabs((double) hi - cc[c]), fabs((double) lo - cc[c])) * fabs(inv_scale)));
+    }
     // centring in fp64: a molecule far from the origin must not lose bits of (p - centroid)
-    if (KIND == KIND_TF32) {
-        float* oh = static_cast<float*>(x_hi_v) + (size_t) r * ld;
-        float* ol = static_cast<float*>(x_lo_v) + (size_t) r * ld;
-        for (int v = tid; v < n0 / 4; v += 256) {
-            const float4 p = *reinterpret_cast<const float4*>(xs + 4 * v);
-            const float e[4] = {p.x, p.y, p.z, p.w};
-            float hi[4], lo[4];
-            int c = (4 * v) % 3;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const double cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
-                split_tf32((float) (((double) e[j] - cc) * inv_scale), hi[j], lo[j]);
-                c = c == 2 ? 0 : c + 1;
+    int e0 = 0;
+    if (KIND == KIND_F16) {
+        // 2^-20 of head-room: `bound` is the exact largest magnitude up to the roundings of the two steps above
+        e0 = exp_for_bound(bound * 1.000001f);
+        if (tid == 0) {
+            chain.x_exp[0][r] = e0;
+            float b = bound;
+            for (int l = 0; l + 2 < net.L; l++) {            // X_{l+1} = act(W_l X_l + b_l)
+                b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
+                chain.x_exp[l + 1][r] = exp_for_bound(b);
             }
-            *reinterpret_cast<float4*>(oh + 4 * v) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(ol + 4 * v) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        ANNF_TGRID_END(dbg);
-        return;
-    }
-    // KIND_F16: the features, then the row's largest magnitude -> its scale exponent, then the scaled pair
-    float mx = 0.f;
-    for (int v = tid; v < n0 / 4; v += 256) {
-        const float4 p = *reinterpret_cast<const float4*>(xs + 4 * v);
-        const float e[4] = {p.x, p.y, p.z, p.w};
-        float x[4];
-        int c = (4 * v) % 3;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const double cc = c == 0 ? c0 : (c == 1 ? c1 : c2);
-            x[j] = (float) (((double) e[j] - cc) * inv_scale);
-            mx = fmaxf(mx, fabsf(x[j]));
-            c = c == 2 ? 0 : c + 1;
-        }
-        *reinterpret_cast<float4*>(xs + 4 * v) = make_float4(x[0], x[1], x[2], x[3]);   // same thread re-reads it below
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) redm[warp] = mx;
-    __syncthreads();
-    mx = redm[0];
-#pragma unroll
-    for (int w = 1; w < 8; w++) mx = fmaxf(mx, redm[w]);
-    const int e0 = exp_for_bound(mx);
-    if (tid == 0) {
-        chain.x_exp[0][r] = e0;
-        float bound = mx;
-        for (int l = 0; l + 2 < net.L; l++) {                // X_{l+1} = act(W_l X_l + b_l)
-            bound = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + bound * chain.fwd_gain[l];
-            chain.x_exp[l + 1][r] = exp_for_bound(bound);
         }
     }
     const float sc = exp2i(e0);
-    __half* oh = static_cast<__half*>(x_hi_v) + (size_t) r * ld;
-    __half* ol = static_cast<__half*>(x_lo_v) + (size_t) r * ld;
-    for (int v = tid; v < n0 / 4; v += 256) {
-        const float4 x = *reinterpret_cast<const float4*>(xs + 4 * v);
-        uint2 hi, lo;
-        split_f16x4(make_float4(x.x * sc, x.y * sc, x.z * sc, x.w * sc), hi, lo);
-        *reinterpret_cast<uint2*>(oh + 4 * v) = hi;
-        *reinterpret_cast<uint2*>(ol + 4 * v) = lo;
+    for (int g = tid; g < quads; g += 256) {
+        const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
+        const float4 p0 = src[0], p1 = src[1], p2 = src[2];
+        const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+        float x[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) x[j] = (float) (((double) e[j] - cc[j % 3]) * inv_scale);
+        if (KIND == KIND_F16) {
+            uint2* oh = reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld) + 3 * g;
+            uint2* ol = reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld) + 3 * g;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                uint2 hi, lo;
+                split_f16x4(make_float4(x[4 * q] * sc, x[4 * q + 1] * sc, x[4 * q + 2] * sc, x[4 * q + 3] * sc), hi, lo);
+                oh[q] = hi;
+                ol[q] = lo;
+            }
+        } else {
+            float4* oh = reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld) + 3 * g;
+            float4* ol = reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld) + 3 * g;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) split_tf32(x[4 * q + j], hi[j], lo[j]);
+                oh[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                ol[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
     }
     if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
     ANNF_TGRID_END(dbg);
@@ -989,6 +1082,7 @@ struct GemmOp {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap b_hi64, b_lo64;          // the same B with 64-row boxes (256 x 128 CTA-pair tiles)
     CUtensorMap a_hi64, a_lo64;          // the same A with 64-row boxes (operand multicast between two N tiles)
+    CUtensorMap out;                     // EPI_FORCE with direct_store: the caller's force array, 32-column x 128-row boxes (per call)
     GemmParams p;
     char name[48];
 };
@@ -1022,6 +1116,7 @@ struct TensorPlan {
     int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
+    bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
 
 static void free_activations(PlanSlot* t) {
@@ -1121,6 +1216,11 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
     if (const char* env = getenv("ANNF_GEMM_SPLIT_SHORTK")) t->force_split = atoi(env);
     if (const char* env = getenv("ANNF_TENSOR_DRY")) t->dry = atoi(env);
+    if (const char* env = getenv("ANNF_TENSOR_DIRECT_STORE")) t->no_direct_store = atoi(env) == 0;
+    // fp16 pairs: one K-block (64 values, 12 chained MMAs) per TMEM chunk; TF32 pairs: two (64 values, 24 chained MMAs).
+    // Measured at BASELINE C5 (64 replicas against the reference, profiles/r02_chunk_sweep.md): the energy error grows with
+    // the chunk length — the tensor core's accumulator truncates — 6.4e-7 / 1.0e-6 / 1.9e-6 / 3.0e-6 worst case at 1 / 2 / 4 / 8.
+    t->chunk = kind == KIND_F16 ? 1 : kChunkDefault;
     if (const char* env = getenv("ANNF_TENSOR_CHUNK")) t->chunk = std::max(1, std::min(64, atoi(env)));
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1293,7 +1393,9 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 template <int KIND, int BN, int S, int CG, int NX = 1>
-static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStream_t stream) {
+static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p_in, cudaStream_t stream) {
+    GemmParams p = p_in;
+    if (S != 1) p.direct_store = 0;
     using Cfg = GemmCfg<BN, CG>;
     static bool configured[64] = {};
     int dev = 0;
@@ -1310,7 +1412,8 @@ static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p, cudaStre
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM * CG - 1) / (BM * CG);
     constexpr bool kBox64 = Cfg::kBRows < 128;
     return launch_pdl(gemm3x_kernel<KIND, BN, S, CG, NX>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG * NX, S,
-                      NX == 2 ? op.a_hi64 : op.a_hi, NX == 2 ? op.a_lo64 : op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo, p);
+                      NX == 2 ? op.a_hi64 : op.a_hi, NX == 2 ? op.a_lo64 : op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo,
+                      p.direct_store ? op.out : op.a_hi, p);
 }
 
 static int pick_split(int tiles, int k_blocks, int sm_count) {
@@ -1320,9 +1423,10 @@ static int pick_split(int tiles, int k_blocks, int sm_count) {
 }
 
 template <int KIND>
-static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStream_t stream, const NetView& net,
+static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaStream_t stream, const NetView& net,
                                float* forces, int atoms_per_replica) {
     constexpr int BK = KindOf<KIND>::kBlockElems;
+    GemmOp op = op_in;
     GemmParams p = op.p;
     p.M = R;
     p.dry = t->dry;
@@ -1333,6 +1437,8 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op, int R, cudaStrea
         p.ld_out = 3 * atoms_per_replica;
         const bool vec_ok = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(forces) & 15) == 0;
         p.sel_atoms = vec_ok ? nullptr : net.sel_atoms;
+        // whole rows, 16-byte aligned: the tile can leave through the TMA engine (fp32 map, 32-column boxes, 128B swizzle)
+        p.direct_store = (vec_ok && !t->no_direct_store && make_map(&op.out, KIND_TF32, forces, R, p.N, p.ld_out, BM)) ? 1 : 0;
     }
     // Tile shape.  CTA pairs (cta_group::2, 256 x 256 tiles): each SM stages 128 rows of A and HALF of the B tile and the MMA
     // reads 25% fewer shared-memory bytes per flop — the two things the 1-CTA kernel is bound by.  They need
