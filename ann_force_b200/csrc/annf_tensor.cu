@@ -1043,6 +1043,388 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused middle of the step (KIND_F16): forward through the last hidden connection, output head, backward through the same
+// connection.  As three kernels (GEMM, head, GEMM) this was 37 of the 90 us of a BASELINE C5 step for 10 % of its flops —
+// three prologues, three first-operand latencies, two launch gaps, a 1024-CTA SIMT kernel in two waves
+// (profiles/r02_c5_phases_session3.txt).  Here a cluster of up to 4 CTAs owns one tile of 128 replicas end to end:
+//   phase 1   CTA j:  A2[:, 128j : 128j+128] = act(X1 W^T + b)       tcgen05 main loop, K = n1
+//   head      every thread-pair of a row: partial output-layer sums over the CTA's 128 columns (fp64), pushed to every CTA of
+//             the cluster through DSMEM, summed in a fixed order; umbrella energy + dE/dz (output_head_parallel);
+//             D2[:, 128j : ...] = (W_L^T dz) (.) act'(A2), scaled and split to fp16 pairs, written to global
+//   phase 2   CTA j:  D1[:, tiles j, j+CL, ..] = (D2 W) (.) act'(X1)   tcgen05 main loop, K = n2 (A through TMA from what the
+//             cluster just wrote: fence.proxy.async + cluster barrier)
+// Warp roles: 8 epilogue warps (two per TMEM lane quarter, 64 accumulator columns each), TMA producer, MMA issuer, a loader
+// for the per-tile vectors, one spare.  One K-block per TMEM chunk, four accumulator buffers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMidCluster = 4;
+constexpr int kMidEpiWarps = 8;
+constexpr int kMidThreads = (kMidEpiWarps + 4) * 32;
+constexpr int kMidStages = 3;
+constexpr int kMidStageBytes = 4 * BM * kBlockBytes;            // A hi, A lo, B hi, B lo: 128 rows x 128 bytes each
+constexpr int kMidDataBytes = kMidStages * kMidStageBytes;      // 192 KB; doubles as the head's scratch and the epilogues' staging
+constexpr int kMidMaxOut = 16;                                  // output nodes the fused head supports
+constexpr int kMidVecBytes = (2 * 128 + 3 * BM) * 4;
+constexpr int kMidSmemBytes = kMidDataBytes + 1024 + 256 + kMidVecBytes;
+// head scratch inside `data` (bytes); zpart is dead once zfull exists and is re-used for dz / energy terms
+constexpr int kMidStagLd = 132;
+constexpr int kMidOffZpart = 68 * 1024;                                        // [4][16][128] doubles = 64 KB
+constexpr int kMidOffZh = kMidOffZpart + kMidCluster * kMidMaxOut * BM * 8;   // [16][128] doubles
+constexpr int kMidOffZfull = kMidOffZh + kMidMaxOut * BM * 8;                  // [16][128] doubles
+constexpr int kMidOffCen = kMidOffZfull + kMidMaxOut * BM * 8;                 // [128][17] doubles
+constexpr int kMidCenLd = kMidMaxOut + 1;
+static_assert(BM * kMidStagLd * 4 <= kMidOffZpart, "staging tile overlaps the head scratch");
+static_assert(kMidOffCen + BM * kMidCenLd * 8 <= kMidDataBytes, "head scratch exceeds the stage buffers");
+constexpr int kMidOffDz = kMidOffZpart;                                        // [16][128] doubles   (aliases zpart)
+constexpr int kMidOffEpart = kMidOffDz + kMidMaxOut * BM * 8;                  // [16][128] doubles
+constexpr int kMidOffDzf = kMidOffEpart + kMidMaxOut * BM * 8;                 // [16][128] floats
+
+struct MidParams {
+    int M, L;
+    int n1, n2, nL;                   // widths of X_{L-3}, X_{L-2} and of the output layer
+    int hidden_type, prev_type, out_type, num_center;
+    const float* bias;                // [n2]   connection L-3
+    const int* w_exp;                 // [n2]   row exponents of W_{L-3}        (B of phase 1)
+    const int* wt_exp;                // [n1]   row exponents of W_{L-3}^T      (B of phase 2)
+    const int* x1_exp;                // [M]    row exponents of X_{L-3}        (A of phase 1, aux of phase 2)
+    const __half *x1_hi, *x1_lo;      // [M][ld1]
+    int ld1;
+    __half *d2_hi, *d2_lo;            // [M][ld2]   D_{L-2}, written here and read back through TMA
+    int ld2;
+    __half *d1_hi, *d1_lo;            // [M][ld1]   D_{L-3}
+    const double* WL;                 // [nL][n2]   output connection, fp64
+    const float* WL32;
+    const double* bL;                 // [nL]
+    const float* centers;             // [M][num_center] or nullptr
+    const double* center_dev;         // [num_center]
+    const double* k_dev;
+    double* energies;                 // [M]
+    int dbg;
+};
+
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t cluster_addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kMidEpiWarps) : "memory"); }
+
+// NLP = output nodes rounded up to 4, 8 or 16: the register accumulators of the partial output-layer sums
+template <int NLP>
+__global__ void __launch_bounds__(kMidThreads, 1)
+mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__ CUtensorMap tm_x1_lo,
+           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+           const __grid_constant__ CUtensorMap tm_d2_hi, const __grid_constant__ CUtensorMap tm_d2_lo,
+           const __grid_constant__ CUtensorMap tm_wt_hi, const __grid_constant__ CUtensorMap tm_wt_lo,
+           const MidParams p, const ExpChain chain) {
+    constexpr int BK = KindOf<KIND_F16>::kBlockElems;
+    constexpr int NB = 4;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* data = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(data + kMidDataBytes);
+    uint64_t* bar_full = bars;                              // [kMidStages]
+    uint64_t* bar_empty = bars + kMidStages;                // [kMidStages]
+    uint64_t* bar_acc_full = bars + 2 * kMidStages;         // [NB]
+    uint64_t* bar_acc_empty = bars + 2 * kMidStages + NB;   // [NB]
+    uint64_t* bar_epi_free = bars + 2 * kMidStages + 2 * NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMidStages + 2 * NB + 1);
+    int* s_b_exp = reinterpret_cast<int*>(data + kMidDataBytes + 256);
+    float* s_bias = reinterpret_cast<float*>(s_b_exp + 128);
+    int* s_a_exp = reinterpret_cast<int*>(s_bias + 128);
+    int* s_out_exp = s_a_exp + BM;
+    int* s_aux_exp = s_out_exp + BM;
+    const EpiVec vec = {s_b_exp, s_bias, s_a_exp, s_out_exp, s_aux_exp};
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int CL = (int) cluster_nctarank();
+    const int rank = (int) cluster_ctarank();               // = blockIdx.x
+    const int m0 = (int) blockIdx.y * BM;
+    const int n0 = rank * 128;                              // this CTA's columns of X_{L-2} / D_{L-2}
+    const int nkb1 = (p.n1 + BK - 1) / BK, nkb2 = (p.n2 + BK - 1) / BK;
+    const int tiles1 = (p.n1 + 127) / 128;                  // output tiles of phase 2; this CTA takes rank, rank + CL, ...
+
+    ANNF_TGRID_START(p.dbg);
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 0);
+    pdl_launch_dependents();
+    if (warp == kMidEpiWarps && lane == 0) {
+        tma_prefetch_desc(&tm_x1_hi); tma_prefetch_desc(&tm_x1_lo); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
+        tma_prefetch_desc(&tm_d2_hi); tma_prefetch_desc(&tm_d2_lo); tma_prefetch_desc(&tm_wt_hi); tma_prefetch_desc(&tm_wt_lo);
+        for (int s = 0; s < kMidStages; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int b = 0; b < NB; b++) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), kMidEpiWarps); }
+        mbar_init(smem_u32(bar_epi_free), kMidEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMidEpiWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (NB * 128)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == kMidEpiWarps + 2) {
+        for (int c = lane; c < 128; c += 32) {              // static vectors of the phase-1 tile
+            const int n = n0 + c;
+            s_b_exp[c] = n < p.n2 ? __ldg(p.w_exp + n) : 0;
+            s_bias[c] = n < p.n2 ? __ldg(p.bias + n) : 0.f;
+        }
+    }
+    tcgen05_fence_before();
+    cluster_barrier();                                      // peers push into this CTA's shared memory later: it must be live
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 1);
+    pdl_wait();
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 2);
+    if (warp == kMidEpiWarps + 2) {
+        for (int r = lane; r < BM; r += 32) s_aux_exp[r] = (m0 + r) < p.M ? p.x1_exp[m0 + r] : 0;
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"n"(32 * (kMidEpiWarps + 1)) : "memory");
+    }
+
+    // ---- pipeline state of the three roles (each role's counters live in its own threads) ----
+    int it = 0;                                             // K-blocks issued / consumed so far (stage ring position)
+    int ch = 0;                                             // TMEM chunks issued / drained so far (accumulator ring position)
+    auto produce = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* b_hi, const CUtensorMap* b_lo, int nkb, int b_row0) {
+        for (int kb = 0; kb < nkb; kb++, it++) {
+            const int s = it % kMidStages;
+            mbar_wait(smem_u32(&bar_empty[s]), (((uint32_t) (it / kMidStages)) & 1u) ^ 1u);
+            const uint32_t full = smem_u32(&bar_full[s]);
+            const uint32_t base = smem_u32(data + (size_t) s * kMidStageBytes);
+            mbar_expect_tx(full, (uint32_t) kMidStageBytes);
+            tma_load_2d(base, a_hi, full, kb * BK, m0);
+            tma_load_2d(base + BM * kBlockBytes, a_lo, full, kb * BK, m0);
+            tma_load_2d(base + 2 * BM * kBlockBytes, b_hi, full, kb * BK, b_row0);
+            tma_load_2d(base + 3 * BM * kBlockBytes, b_lo, full, kb * BK, b_row0);
+        }
+    };
+    auto issue = [&](int nkb) {
+        constexpr uint32_t idesc = umma_idesc_mn(KIND_F16, BM, 128);
+        for (int kb = 0; kb < nkb; kb++, it++, ch++) {
+            const int buf = ch % NB, s = it % kMidStages;
+            mbar_wait(smem_u32(&bar_acc_empty[buf]), (((uint32_t) (ch / NB)) & 1u) ^ 1u);
+            mbar_wait(smem_u32(&bar_full[s]), ((uint32_t) (it / kMidStages)) & 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * 128);
+            const uint32_t base = smem_u32(data + (size_t) s * kMidStageBytes);
+            const uint32_t a_hi = base, a_lo = base + BM * kBlockBytes, b_hi = base + 2 * BM * kBlockBytes, b_lo = base + 3 * BM * kBlockBytes;
+#pragma unroll
+            for (int kk = 0; kk < kStepsPerBlock; kk++) {
+                const uint32_t off = kk * kStepBytes;
+                const uint64_t dah = umma_smem_desc(a_hi + off), dal = umma_smem_desc(a_lo + off);
+                const uint64_t dbh = umma_smem_desc(b_hi + off), dbl = umma_smem_desc(b_lo + off);
+                umma_mma<KIND_F16>(tmem_acc, dal, dbh, idesc, kk == 0 ? 0u : 1u);     // small terms first
+                umma_mma<KIND_F16>(tmem_acc, dah, dbl, idesc, 1u);
+                umma_mma<KIND_F16>(tmem_acc, dah, dbh, idesc, 1u);
+            }
+            umma_commit(smem_u32(&bar_empty[s]));
+            umma_commit(smem_u32(&bar_acc_full[buf]));
+        }
+    };
+    // epilogue threads: e = 0..255; TMEM lane quarter q, column half h of the CTA's 128 columns
+    const int e = (int) threadIdx.x, q = warp & 3, h = warp >> 2, row = q * 32 + lane;
+    float acc[64];
+    auto drain = [&](int nkb) {
+#pragma unroll
+        for (int j = 0; j < 64; j++) acc[j] = 0.f;
+        for (int kb = 0; kb < nkb; kb++, ch++) {
+            const int buf = ch % NB;
+            mbar_wait(smem_u32(&bar_acc_full[buf]), ((uint32_t) (ch / NB)) & 1u);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (buf * 128 + h * 64 + cc * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[cc * 32 + j] += __uint_as_float(r[j]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_acc_empty[buf])) : "memory");
+        }
+        // park this thread's 64 columns of its row (the stage buffers are free: every MMA of the tile has completed)
+        float* dst = reinterpret_cast<float*>(data) + (size_t) row * kMidStagLd + h * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    };
+
+    float* stag = reinterpret_cast<float*>(data);
+    double* zpart = reinterpret_cast<double*>(data + kMidOffZpart);
+    double* zh = reinterpret_cast<double*>(data + kMidOffZh);
+    double* zfull = reinterpret_cast<double*>(data + kMidOffZfull);
+    double* cen = reinterpret_cast<double*>(data + kMidOffCen);
+    double* dzs = reinterpret_cast<double*>(data + kMidOffDz);
+    double* epart = reinterpret_cast<double*>(data + kMidOffEpart);
+    float* dzf = reinterpret_cast<float*>(data + kMidOffDzf);
+
+    // =========================== phase 1: A2 slice, partial output-layer sums ===========================
+    if (warp == kMidEpiWarps) {
+        if (lane == 0) produce(&tm_x1_hi, &tm_x1_lo, &tm_w_hi, &tm_w_lo, nkb1, n0);
+        __syncwarp();
+    } else if (warp == kMidEpiWarps + 1) {
+        if (lane == 0) issue(nkb1);
+        __syncwarp();
+    } else if (warp < kMidEpiWarps) {
+        drain(nkb1);
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 3);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * (kMidEpiWarps + 1)) : "memory");   // staged vectors are in place
+        const int ea = s_aux_exp[row];
+        float* mine = stag + (size_t) row * kMidStagLd + h * 64;
+        double zacc[NLP];
+#pragma unroll
+        for (int j = 0; j < NLP; j++) zacc[j] = 0.0;
+        // rolled on purpose (instruction-cache footprint): 16 groups of 4 columns of this thread's row half
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) {
+            const int lc = h * 64 + 4 * i, n = n0 + lc;
+            float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
+            const int4 eb = *reinterpret_cast<const int4*>(s_b_exp + lc);
+            const float4 bs = *reinterpret_cast<const float4*>(s_bias + lc);
+            v.x = v.x * exp2i(-(ea + eb.x)) + bs.x; v.y = v.y * exp2i(-(ea + eb.y)) + bs.y;
+            v.z = v.z * exp2i(-(ea + eb.z)) + bs.z; v.w = v.w * exp2i(-(ea + eb.w)) + bs.w;
+            if (p.hidden_type == ANNF_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            *reinterpret_cast<float4*>(mine + 4 * i) = v;                          // A2 stays here for act'() below
+            if (n < p.n2) {                                                        // n2 is a multiple of 4: a group is all in or all out
+#pragma unroll
+                for (int j = 0; j < NLP; j++) {
+                    if (j < p.nL) {
+                        const double2 w0 = __ldg(reinterpret_cast<const double2*>(p.WL + (size_t) j * p.n2 + n));
+                        const double2 w1 = __ldg(reinterpret_cast<const double2*>(p.WL + (size_t) j * p.n2 + n + 2));
+                        zacc[j] = fma(w0.x, (double) v.x, zacc[j]); zacc[j] = fma(w0.y, (double) v.y, zacc[j]);
+                        zacc[j] = fma(w1.x, (double) v.z, zacc[j]); zacc[j] = fma(w1.y, (double) v.w, zacc[j]);
+                    }
+                }
+            }
+        }
+        // the two column halves of a row, then push this CTA's partial sums to every CTA of the cluster
+        if (h == 1) {
+#pragma unroll
+            for (int j = 0; j < NLP; j++) if (j < p.nL) zh[j * BM + row] = zacc[j];
+        }
+        epi_barrier();
+        if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < NLP; j++) {
+                if (j < p.nL) {
+                    const double z = zacc[j] + zh[j * BM + row];
+                    const uint32_t local = smem_u32(zpart + ((size_t) rank * kMidMaxOut + j) * BM + row);
+                    for (int c = 0; c < CL; c++) st_cluster_f64(map_to_cta(local, (uint32_t) c), z);
+                }
+            }
+        }
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 4);
+    }
+    cluster_barrier();                                      // A: every CTA holds every partial sum
+    // =========================== head: energy, dE/dz, D2 slice ===========================
+    if (warp < kMidEpiWarps) {
+        for (int v = e; v < p.nL * BM; v += 32 * kMidEpiWarps) {
+            const int j = v / BM, r = v % BM;
+            double z = p.bL[j];
+            for (int c = 0; c < CL; c++) z += zpart[((size_t) c * kMidMaxOut + j) * BM + r];   // fixed order: deterministic
+            zfull[j * BM + r] = z;
+        }
+        for (int v = e; v < p.num_center * BM; v += 32 * kMidEpiWarps) {
+            const int c = v / BM, r = v % BM, m = m0 + r;
+            cen[r * kMidCenLd + c] = (p.centers != nullptr && m < p.M) ? (double) p.centers[(size_t) m * p.num_center + c] : p.center_dev[c];
+        }
+        epi_barrier();
+        const double kforce = *p.k_dev;
+        for (int v = e; v < kMidMaxOut * BM; v += 32 * kMidEpiWarps) {            // item (t, r): output t (or Circular pair t) of row r
+            const int t = v / BM, r = v % BM;
+            if (t < p.nL) epart[t * BM + r] = output_head_parallel(p.out_type, p.nL, zfull + r, BM, cen + r * kMidCenLd, kforce, dzs + r, BM, t);
+        }
+        epi_barrier();
+        if (e < BM) {                                       // one thread per row: energy, scale exponents of the gradient rows
+            const int r = e, m = m0 + r;
+            double en = 0.0;
+            float mx = 0.f;
+            for (int j = 0; j < p.nL; j++) {
+                en += epart[j * BM + r];
+                const float d = (float) dzs[j * BM + r];
+                dzf[j * BM + r] = d;
+                mx = fmaxf(mx, fabsf(d));
+            }
+            float bound = mx * chain.bwd_gain[p.L - 2];     // |D2[r][.]| <= max_j |dz_j| * max column L1 norm of W_L
+            const int e2 = exp_for_bound(bound);
+            bound *= chain.bwd_gain[p.L - 3];               // |D1[r][.]| <= the same through W_{L-3}, |act'| <= 1
+            const int e1 = exp_for_bound(bound);
+            s_a_exp[r] = e2;                                // A rows of phase 2
+            s_out_exp[r] = e1;                              // rows coming out of phase 2
+            if (rank == 0 && m < p.M) {
+                p.energies[m] = en;
+                chain.d_exp[p.L - 2][m] = e2;
+                chain.d_exp[p.L - 3][m] = e1;
+                for (int l = p.L - 4; l >= 1; l--) {        // deeper networks: the rest of the chain, like head_kernel
+                    bound *= chain.bwd_gain[l];
+                    chain.d_exp[l][m] = exp_for_bound(bound);
+                }
+            }
+        }
+        epi_barrier();
+        // D2 slice: lanes along a row (coalesced stores), 32 four-column groups per row
+#pragma unroll 1
+        for (int v = e; v < BM * 32; v += 32 * kMidEpiWarps) {
+            const int r = v >> 5, lc = (v & 31) * 4, n = n0 + lc, m = m0 + r;
+            if (m >= p.M || n >= p.n2) continue;
+            const float4 a = *reinterpret_cast<const float4*>(stag + (size_t) r * kMidStagLd + lc);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < p.nL; j++) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(p.WL32 + (size_t) j * p.n2 + n));
+                const float d = dzf[j * BM + r];
+                g.x = fmaf(w.x, d, g.x); g.y = fmaf(w.y, d, g.y); g.z = fmaf(w.z, d, g.z); g.w = fmaf(w.w, d, g.w);
+            }
+            if (p.hidden_type == ANNF_TANH) { g.x *= (1.f - a.x * a.x); g.y *= (1.f - a.y * a.y); g.z *= (1.f - a.z * a.z); g.w *= (1.f - a.w * a.w); }
+            const float sc = exp2i(s_a_exp[r]);
+            uint2 hi, lo;
+            split_f16x4(make_float4(g.x * sc, g.y * sc, g.z * sc, g.w * sc), hi, lo);
+            *reinterpret_cast<uint2*>(p.d2_hi + (size_t) m * p.ld2 + n) = hi;
+            *reinterpret_cast<uint2*>(p.d2_lo + (size_t) m * p.ld2 + n) = lo;
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy global writes -> visible to the TMA loads of phase 2
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 5);
+    }
+    cluster_barrier();                                      // B: D2 is complete for this tile of replicas
+    // =========================== phase 2: D1 tiles ===========================
+    if (warp == kMidEpiWarps) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            int done = 0;
+            for (int t = rank; t < tiles1; t += CL, done++) {
+                if (done > 0) mbar_wait(smem_u32(bar_epi_free), ((uint32_t) (done - 1)) & 1u);   // the epilogue's staging overlaps the stages
+                produce(&tm_d2_hi, &tm_d2_lo, &tm_wt_hi, &tm_wt_lo, nkb2, t * 128);
+            }
+        }
+    } else if (warp == kMidEpiWarps + 1) {
+        if (lane == 0)
+            for (int t = rank; t < tiles1; t += CL) issue(nkb2);
+    } else if (warp < kMidEpiWarps) {
+        GemmParams gp;
+        gp.M = p.M; gp.N = p.n1; gp.K = p.n2;
+        gp.epi = p.prev_type == ANNF_TANH ? EPI_TANH_GRAD : EPI_LINEAR_GRAD;
+        gp.bias = nullptr;
+        gp.aux_hi = p.x1_hi; gp.aux_lo = p.x1_lo; gp.ld_aux = p.ld1;
+        gp.out_hi = p.d1_hi; gp.out_lo = p.d1_lo; gp.ld_out = p.ld1;
+        gp.a_exp = nullptr; gp.b_exp = nullptr; gp.out_exp = nullptr; gp.aux_exp = nullptr;   // staged in `vec`
+        gp.sel_atoms = nullptr; gp.direct_store = 0; gp.dbg = -1; gp.chunk = 1; gp.dry = 0;
+        for (int t = rank; t < tiles1; t += CL) {
+            drain(nkb2);
+            if (e < 128) s_b_exp[e] = (t * 128 + e) < p.n1 ? __ldg(p.wt_exp + t * 128 + e) : 0;
+            epi_barrier();                                  // tile parked, column exponents staged
+            if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 7);
+            cooperative_epilogue<KIND_F16, 128, 1, 1, 32 * kMidEpiWarps, 1>(gp, vec, data, 0, 0, m0, t * 128, e);
+            if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
+            epi_barrier();                                  // staging and s_b_exp may be overwritten by the next tile
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_epi_free)) : "memory");
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
+    if (warp == kMidEpiWarps + 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (NB * 128)) : "memory");
+    }
+    ANNF_TGRID_END(p.dbg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side: plan
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1116,6 +1498,7 @@ struct TensorPlan {
     int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
+    bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
 
@@ -1268,6 +1651,9 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
             return no("out of device memory for the tensor-core weight copies");
         }
     }
+    // the fused middle kernel: fp16 pairs, two or more hidden layers, last hidden layer within one 4-CTA cluster, few outputs
+    t->use_mid = kind == KIND_F16 && L >= 4 && net.nodes[L - 2] <= 128 * kMidCluster && net.nodes[L - 1] <= kMidMaxOut;
+    if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = t->use_mid && atoi(env) != 0;
     // fp32 biases live in NetView::b32 already
     {
         std::vector<int> sel(net.n_sel);
@@ -1479,8 +1865,12 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
         const int pair_ctas = 2 * ((p.N + 127) / 128) * ((R + 255) / 256);
         int s = std::min(4, pick_split(pair_ctas, kb, t->sm_count));
         if (t->force_split > 0 && kb <= 32) s = std::min(4, t->force_split);
+        // 2 x 4 clusters: a B200 co-schedules 15 of them, so 16 run in two waves; 2 x 3 clusters (96 CTAs at C5) fit in one
+        if (s == 4 && pair_ctas / 2 > 15) s = 3;
+        if (const char* env = getenv("ANNF_GEMM_PAIR_SPLIT")) s = atoi(env);
         switch (s) {
         case 4: return launch_gemm_t<KIND, 128, 4, 2>(op, p, stream);
+        case 3: return launch_gemm_t<KIND, 128, 3, 2>(op, p, stream);
         case 2: return launch_gemm_t<KIND, 128, 2, 2>(op, p, stream);
         default: return launch_gemm_t<KIND, 128, 1, 2>(op, p, stream);
         }
@@ -1523,6 +1913,45 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
     }
 }
 
+template <int NLP>
+static cudaError_t launch_mid_t(const GemmOp& fwd, const GemmOp& bwd, const MidParams& mp, const ExpChain& chain, int cl, int m_tiles, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t err = cudaFuncSetAttribute(mid_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMidSmemBytes);
+        if (err != cudaSuccess) return err;
+        configured[dev] = true;
+    }
+    return launch_pdl(mid_kernel<NLP>, dim3(cl, m_tiles, 1), dim3(kMidThreads), kMidSmemBytes, stream, cl, 1,
+                      fwd.a_hi, fwd.a_lo, fwd.b_hi, fwd.b_lo, bwd.a_hi, bwd.a_lo, bwd.b_hi, bwd.b_lo, mp, chain);
+}
+
+static cudaError_t launch_mid(TensorPlan* t, PlanSlot* sl, const NetView& net, int R, const float* centers, double* energies,
+                              const ExpChain& chain, cudaStream_t stream) {
+    const int L = t->L;
+    MidParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.M = R; mp.L = L;
+    mp.n1 = t->nodes[L - 3]; mp.n2 = t->nodes[L - 2]; mp.nL = t->nodes[L - 1];
+    mp.hidden_type = t->types[L - 3]; mp.prev_type = t->types[L - 4]; mp.out_type = t->types[L - 2]; mp.num_center = net.num_center;
+    mp.bias = net.b32 + net.b_off[L - 3];
+    mp.w_exp = t->w_exp[L - 3]; mp.wt_exp = t->wt_exp[L - 3]; mp.x1_exp = sl->x_exp[L - 3];
+    mp.x1_hi = static_cast<const __half*>(sl->x_hi[L - 3]); mp.x1_lo = static_cast<const __half*>(sl->x_lo[L - 3]); mp.ld1 = t->ld[L - 3];
+    mp.d2_hi = static_cast<__half*>(sl->d_hi[L - 2]); mp.d2_lo = static_cast<__half*>(sl->d_lo[L - 2]); mp.ld2 = t->ld[L - 2];
+    mp.d1_hi = static_cast<__half*>(sl->d_hi[L - 3]); mp.d1_lo = static_cast<__half*>(sl->d_lo[L - 3]);
+    mp.WL = net.W64 + net.w_off[L - 2]; mp.WL32 = net.W32 + net.w_off[L - 2]; mp.bL = net.b64 + net.b_off[L - 2];
+    mp.centers = centers; mp.center_dev = net.center; mp.k_dev = net.k_dev; mp.energies = energies;
+    mp.dbg = t->dbg_next < 8 ? t->dbg_next++ : -1;
+    const GemmOp& fwd = sl->fwd[L - 3];               // forward connection L-3: A = X_{L-3}, B = W_{L-3}
+    const GemmOp& bwd = sl->bwd[0];                   // backward connection L-3: A = D_{L-2}, B = W_{L-3}^T
+    const int cl = mp.n2 <= 128 ? 1 : (mp.n2 <= 256 ? 2 : 4);
+    const int m_tiles = (R + BM - 1) / BM;
+    if (mp.nL <= 4) return launch_mid_t<4>(fwd, bwd, mp, chain, cl, m_tiles, stream);
+    if (mp.nL <= 8) return launch_mid_t<8>(fwd, bwd, mp, chain, cl, m_tiles, stream);
+    return launch_mid_t<16>(fwd, bwd, mp, chain, cl, m_tiles, stream);
+}
+
 template <int KIND>
 static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net, int R, const float* coords,
                               int atoms_per_replica, const float* centers, float* forces, double* energies,
@@ -1546,17 +1975,26 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
                           sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain, t->dbg_next++);
     });
     if (err != cudaSuccess) return err;
-    for (const GemmOp& op : sl->fwd) {
+    const bool mid = KIND == KIND_F16 && t->use_mid;
+    for (size_t i = 0; i < sl->fwd.size(); i++) {
+        if (mid && i + 1 == sl->fwd.size()) break;        // the last hidden connection belongs to the fused middle kernel
+        const GemmOp& op = sl->fwd[i];
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
         err = timed(name, [&] { return launch_gemm<KIND>(t, op, R, stream, net, nullptr, 0); });
         if (err != cudaSuccess) return err;
     }
+    if (mid) {
+        snprintf(name, sizeof(name), "mid[%dx%dx%d] fwd%d+head+bwd%d", R, t->nodes[L - 2], t->nodes[L - 3], L - 3, L - 3);
+        err = timed(name, [&] { return launch_mid(t, sl, net, R, centers, energies, chain, stream); });
+        if (err != cudaSuccess) return err;
+    } else
     err = timed("head_kernel", [&] {
         return launch_pdl(head_kernel<KIND>, dim3(R), dim3(kHeadThreads), 0, stream, 1, 0, net, t->dry ? -R : R, centers, (const void*) sl->x_hi[L - 2],
                           (const void*) sl->x_lo[L - 2], t->ld[L - 2], sl->d_hi[L - 2], sl->d_lo[L - 2], energies, chain, t->dbg_next < 8 ? t->dbg_next++ : -1);
     });
     if (err != cudaSuccess) return err;
-    for (const GemmOp& op : sl->bwd) {
+    for (size_t i = mid ? 1 : 0; i < sl->bwd.size(); i++) {
+        const GemmOp& op = sl->bwd[i];
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
         err = timed(name, [&] { return launch_gemm<KIND>(t, op, R, stream, net, forces, atoms_per_replica); });
         if (err != cudaSuccess) return err;

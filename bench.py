@@ -463,7 +463,7 @@ def main():
         avg_ms = rec["total_ms"] / max(rec["launches"], 1)
         kflops = kernel_flops(name, nodes, R, flops_eval)
         latency_bound = args.workload != "c5"
-        if name.startswith("gemm[") and "f16x3" in name:
+        if (name.startswith("gemm[") and "f16x3" in name) or name.startswith("mid["):
             # tcgen05 kind::f16 on fp16 pairs: the dense fp16/bf16 tensor peak.  Burst figure: the kernel is timed alone,
             # one event pair per launch.  A three-product kernel tops out at frac 1/3.
             bound = "tensor"
@@ -591,6 +591,10 @@ def fp64_probe_line():
 
 def kernel_flops(name, nodes, R, flops_eval):
     """Algorithmic flops of one launch of the named kernel."""
+    if name.startswith("mid["):
+        # fused forward + head + backward of one hidden connection: two GEMMs of the named shape (the head is O(n))
+        m, n, k = (int(v) for v in name[4:name.index("]")].split("x"))
+        return 2.0 * 2.0 * m * n * k
     if name.startswith("gemm["):
         # tensor path names its GEMMs gemm[MxNxK]...
         m, n, k = (int(v) for v in name[5:name.index("]")].split("x"))

@@ -256,6 +256,10 @@ def test_wide_network_properties_and_sampled_parity():
     ([300, 128, 4], ["Tanh", "Softmax"], 1),                     # one hidden layer, single replica, Softmax head
     ([1536, 256, 256, 2], ["Tanh", "Tanh", "Linear"], 384),      # three M tiles
     ([4500, 512, 512, 8], ["Tanh", "Tanh", "Tanh"], 600),        # BASELINE C5 widths: CTA-pair GEMMs, 2 x 8 clusters, ragged M
+    ([300, 128, 96, 6], ["Tanh", "Tanh", "Softmax"], 70),        # fused middle kernel: Softmax head, one-CTA cluster
+    ([900, 640, 128, 4], ["Tanh", "Linear", "Tanh"], 140),       # fused middle kernel: five backward tiles per CTA, Linear last hidden layer
+    ([600, 256, 256, 128, 3], ["Tanh", "Tanh", "Tanh", "Linear"], 130),   # three hidden layers: GEMM, GEMM, fused middle, GEMM, GEMM
+    ([300, 128, 320, 16], ["Tanh", "Tanh", "Circular"], 260),    # 16 outputs (8 angles), last hidden layer over 3 of 4 cluster CTAs
 ])
 @pytest.mark.parametrize("precision", TENSOR_KINDS)
 def test_tensor_core_path_matches_oracle(nodes, types, R, precision):
@@ -466,6 +470,28 @@ def test_large_replica_count_and_padded_rows():
     e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
     np.testing.assert_allclose(e[sample], e_ref, rtol=1e-11)
     assert max_norm_rel(f[sample][:, :7], f_ref[:, :7]) <= 1e-6
+
+
+def test_fused_middle_kernel_matches_the_three_kernel_path(monkeypatch):
+    """f16x3 with the last hidden connection + head + its backward in ONE kernel (default) against the same step as GEMM,
+    head kernel, GEMM (ANNF_TENSOR_MID=0): same arithmetic except for the order of the output-layer partial sums, so the
+    two agree far inside the parity bar; and both are deterministic run to run."""
+    nodes, types, R = [1200, 512, 512, 8], ["Tanh", "Tanh", "Tanh"], 300
+    force = synthetic.make_force(nodes, types, 400, seed=91)
+    pos = synthetic.make_positions(400, R, seed=92)
+    cen = synthetic.make_centers(force, R, seed=93)
+    e_mid, f_mid, _ = run_batched(force, pos, cen, precision="f16x3")
+    e_mid2, f_mid2, _ = run_batched(force, pos, cen, precision="f16x3")
+    np.testing.assert_array_equal(e_mid, e_mid2)
+    np.testing.assert_array_equal(f_mid, f_mid2)
+    monkeypatch.setenv("ANNF_TENSOR_MID", "0")
+    e_sep, f_sep, _ = run_batched(force, pos, cen, precision="f16x3")
+    np.testing.assert_allclose(e_mid, e_sep, rtol=2e-6)
+    assert max_norm_rel(f_mid, f_sep) <= 1e-5
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    np.testing.assert_allclose(e_sep, e_ref, rtol=2e-5)
+    np.testing.assert_allclose(e_mid, e_ref, rtol=2e-5)
+    assert max_norm_rel(f_mid, f_ref) <= F_RTOL
 
 
 @pytest.mark.parametrize("precision", TENSOR_KINDS)

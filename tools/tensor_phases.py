@@ -31,7 +31,7 @@ en = torch.empty(R, dtype=torch.float64, device="cuda")
 for i in range(16):
     k.execute_batched(coords[i % 8], cen, out[i % 8], en)
 torch.cuda.synchronize()
-names = ["prep", "fwd0", "fwd1", "head", "bwd1", "bwd0", "k6", "k7"]
+names = ["k0", "k1", "k2", "k3", "k4", "k5", "k6", "k7"]   # launch order: prep, forward GEMMs, (fused middle | GEMM, head, GEMM), backward GEMMs
 phase = ["entry", "prologue", "deps", "tma0", "landed0", "mma_done", "drained", "parked", "epilogue", "exit"]
 buf = (C.c_int64 * 192)()
 for rep in range(3):
