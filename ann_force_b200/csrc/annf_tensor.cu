@@ -41,6 +41,7 @@
 
 #include "annf_common.cuh"
 #include "annf_profiler.h"
+#include "annf_ptx.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -793,13 +794,14 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
     if (contiguous & 2) return;                             // experiments: launch-floor dry run
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;         // 128 or 256 (ANNF_PREP_THREADS)
     const int A = net.n_sel, quads = A / 4;
     const float* base = coords + (size_t) r * N * 3;
     __shared__ double red_sum[8][3];
     __shared__ float red_min[8][3], red_max[8][3];
     double s[3] = {0.0, 0.0, 0.0};
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int g = tid; g < quads; g += 256) {
+    for (int g = tid; g < quads; g += nthreads) {
         float e[12];
         if (contiguous & 1) {
             // selection is atoms 0..A-1 and rows are 16-byte aligned: three vector loads per 4 atoms
@@ -848,7 +850,8 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
         double t = 0.0;
         float lo = 3.0e38f, hi = -3.0e38f;
 #pragma unroll
-        for (int w = 0; w < 8; w++) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
+        for (int w = 0; w < 8; w++)
+            if (w < nwarps) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
         cc[c] = t / A;                                       // centroid of the unscaled coordinates
         bound = fmaxf(bound, (float) (fmax(fabs((double) hi - cc[c]), fabs((double) lo - cc[c])) * fabs(inv_scale)));
     }
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
         }
     }
     const float sc = exp2i(e0);
-    for (int g = tid; g < quads; g += 256) {
+    for (int g = tid; g < quads; g += nthreads) {
         const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
         const float4 p0 = src[0], p1 = src[1], p2 = src[2];
         const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
@@ -901,6 +904,115 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     ANNF_TGRID_END(dbg);
 }
 
+// prep, persistent flavour (KIND_F16, selection = atoms 0..A-1, 16-byte aligned rows — the BASELINE C5 case): 2 CTAs per SM walk
+// the replicas; the NEXT row of coordinates arrives by one bulk copy (TMA engine, mbarrier) while the current one is reduced,
+// centred, scaled and split.  The one-CTA-per-replica kernel above is a chain of dependent phases per CTA — load, reduce,
+// barrier, convert, store — that all 1024 CTAs walk in lock-step: 12.9 us for 18 MB in and 18 MB out (profiles/r02_c5_phases_*).
+constexpr int kPrepPipeThreads = 256;
+__global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetView net, int R, const float* __restrict__ coords, int N,
+                                                                       __half* __restrict__ x_hi, __half* __restrict__ x_lo, int ld,
+                                                                       ExpChain chain, int dbg) {
+    extern __shared__ __align__(128) unsigned char prep_smem[];
+    const int A = net.n_sel, quads = A / 4, row_bytes = 12 * A;      // 3A floats; A % 4 == 0, so a row is a multiple of 48 bytes
+    const int buf_stride = (row_bytes + 127) & ~127;
+    __shared__ uint64_t bar[2];
+    __shared__ double red_sum[8][3];
+    __shared__ float red_min[8][3], red_max[8][3];
+    ANNF_TGRID_START(dbg);
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 0);
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        ptx::bar_init(ptx::s_u32(&bar[0]), 1);
+        ptx::bar_init(ptx::s_u32(&bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
+    const double inv_scale = 1.0 / net.scale;
+    int r = blockIdx.x;
+    if (r < R && tid == 0) {
+        ptx::bar_expect_tx(ptx::s_u32(&bar[0]), (uint32_t) row_bytes);
+        ptx::bulk_load(ptx::s_u32(prep_smem), coords + (size_t) r * N * 3, (uint32_t) row_bytes, ptx::s_u32(&bar[0]));
+    }
+    for (int i = 0; r < R; i++, r += gridDim.x) {
+        const int cur = i & 1, rn = r + gridDim.x;
+        if (rn < R && tid == 0) {                           // buffer cur ^ 1 was released by the barrier that ended iteration i - 1
+            ptx::bar_expect_tx(ptx::s_u32(&bar[cur ^ 1]), (uint32_t) row_bytes);
+            ptx::bulk_load(ptx::s_u32(prep_smem + (size_t) (cur ^ 1) * buf_stride), coords + (size_t) rn * N * 3, (uint32_t) row_bytes, ptx::s_u32(&bar[cur ^ 1]));
+        }
+        ptx::bar_wait(ptx::s_u32(&bar[cur]), (uint32_t) (i >> 1) & 1u);
+        const float4* src = reinterpret_cast<const float4*>(prep_smem + (size_t) cur * buf_stride);
+        double s[3] = {0.0, 0.0, 0.0};
+        float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        for (int g = tid; g < quads; g += kPrepPipeThreads) {
+            const float4 p0 = src[3 * g], p1 = src[3 * g + 1], p2 = src[3 * g + 2];
+            const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                s[c] += ((double) e[c] + (double) e[3 + c]) + ((double) e[6 + c] + (double) e[9 + c]);
+                mn[c] = fminf(fminf(mn[c], fminf(e[c], e[3 + c])), fminf(e[6 + c], e[9 + c]));
+                mx[c] = fmaxf(fmaxf(mx[c], fmaxf(e[c], e[3 + c])), fmaxf(e[6 + c], e[9 + c]));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            s[c] = warp_sum(s[c]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { red_sum[warp][c] = s[c]; red_min[warp][c] = mn[c]; red_max[warp][c] = mx[c]; }
+        }
+        __syncthreads();
+        double cc[3];
+        float bound = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double t = 0.0;
+            float lo = 3.0e38f, hi = -3.0e38f;
+#pragma unroll
+            for (int w = 0; w < kPrepPipeThreads / 32; w++) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
+            cc[c] = t / A;
+            bound = fmaxf(bound, (float) (fmax(fabs((double) hi - cc[c]), fabs((double) lo - cc[c])) * fabs(inv_scale)));
+        }
+        const int e0 = exp_for_bound(bound * 1.000001f);
+        if (tid == 0) {
+            chain.x_exp[0][r] = e0;
+            float b = bound;
+            for (int l = 0; l + 2 < net.L; l++) {
+                b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
+                chain.x_exp[l + 1][r] = exp_for_bound(b);
+            }
+        }
+        const float sc = exp2i(e0);
+        uint2* oh = reinterpret_cast<uint2*>(x_hi + (size_t) r * ld);
+        uint2* ol = reinterpret_cast<uint2*>(x_lo + (size_t) r * ld);
+        for (int g = tid; g < quads; g += kPrepPipeThreads) {
+            const float4 p0 = src[3 * g], p1 = src[3 * g + 1], p2 = src[3 * g + 2];
+            const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+            float x[12];
+#pragma unroll
+            for (int j = 0; j < 12; j++) x[j] = (float) (((double) e[j] - cc[j % 3]) * inv_scale) * sc;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                uint2 hi, lo;
+                split_f16x4(make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), hi, lo);
+                oh[3 * g + q] = hi;
+                ol[3 * g + q] = lo;
+            }
+        }
+        __syncthreads();                                    // buf[cur] and the reduction scratch are free again
+    }
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
+    ANNF_TGRID_END(dbg);
+}
+
 // activation m of a row stored as an operand pair: hi + lo is exact in fp32, and so is the power-of-two unscale
 template <int KIND>
 __device__ __forceinline__ float load_pair(const void* hi, const void* lo, int m, float unscale) {
@@ -918,8 +1030,9 @@ __device__ __forceinline__ float load_pair(const void* hi, const void* lo, int m
 // that runs once per CTA; rolled, its 128 fat CTAs delayed the cluster GEMM that follows under PDL: step 110 -> 121 us.)
 constexpr int kHeadThreads = 128;
 constexpr int kHeadMaxOut = 64;
+constexpr int kHeadBatch = 2;
 template <int KIND>
-__global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, const float* __restrict__ centers,
+__global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int R, const float* __restrict__ centers,
                                                            const void* __restrict__ a_hi, const void* __restrict__ a_lo, int ld,
                                                            void* __restrict__ d_hi, void* __restrict__ d_lo, double* __restrict__ energies,
                                                            ExpChain chain, int dbg) {
@@ -942,22 +1055,23 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(NetView net, int R, 
     const elem* ah = static_cast<const elem*>(a_hi) + (size_t) r * ld;
     const elem* al = static_cast<const elem*>(a_lo) + (size_t) r * ld;
     const float a_unscale = KIND == KIND_F16 ? exp2i(-chain.x_exp[L - 2][r]) : 1.f;
-    // The loop is bound by global-load latency unless many loads are in flight: four hidden units per thread per pass, their
-    // activations and 4 x 8 weights all loaded before the 32 dependent fp64 FMAs.
+    // The loop is bound by global-load latency unless many loads are in flight: kHeadBatch hidden units per thread per pass, their
+    // activations and kHeadBatch x 8 weights all loaded before the dependent fp64 FMAs.  Two, not four: 7 CTAs per SM (72 registers)
+    // keep all 1024 CTAs of a BASELINE C5 batch resident at once; at 96 registers they ran in two waves.
     for (int j0 = 0; j0 < nL; j0 += 8) {                    // 8 outputs at a time: 8 independent accumulators per thread
         double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int mb = tid; mb < nH; mb += 4 * kHeadThreads) {
-            float av[4];
-            double w[4][8];
+        for (int mb = tid; mb < nH; mb += kHeadBatch * kHeadThreads) {
+            float av[kHeadBatch];
+            double w[kHeadBatch][8];
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
+            for (int v = 0; v < kHeadBatch; v++) {
                 const int m = mb + v * kHeadThreads;
                 av[v] = m < nH ? load_pair<KIND>(ah, al, m, a_unscale) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 8; u++) w[v][u] = (m < nH && j0 + u < nL) ? __ldg(W + (size_t) (j0 + u) * nH + m) : 0.0;
             }
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
+            for (int v = 0; v < kHeadBatch; v++) {
                 const double a = (double) av[v];
 #pragma unroll
                 for (int u = 0; u < 8; u++) acc[u] = fma(w[v][u], a, acc[u]);
@@ -1266,6 +1380,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         drain(nkb1);
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 3);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * (kMidEpiWarps + 1)) : "memory");   // staged vectors are in place
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 10);
         const int ea = s_aux_exp[row];
         float* mine = stag + (size_t) row * kMidStagLd + h * 64;
         double zacc[NLP];
@@ -1294,12 +1409,14 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
                 }
             }
         }
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 11);
         // the two column halves of a row, then push this CTA's partial sums to every CTA of the cluster
         if (h == 1) {
 #pragma unroll
             for (int j = 0; j < NLP; j++) if (j < p.nL) zh[j * BM + row] = zacc[j];
         }
         epi_barrier();
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 12);
         if (h == 0) {
 #pragma unroll
             for (int j = 0; j < NLP; j++) {
@@ -1313,6 +1430,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 4);
     }
     cluster_barrier();                                      // A: every CTA holds every partial sum
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 13);
     // =========================== head: energy, dE/dz, D2 slice ===========================
     if (warp < kMidEpiWarps) {
         for (int v = e; v < p.nL * BM; v += 32 * kMidEpiWarps) {
@@ -1326,12 +1444,14 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
             cen[r * kMidCenLd + c] = (p.centers != nullptr && m < p.M) ? (double) p.centers[(size_t) m * p.num_center + c] : p.center_dev[c];
         }
         epi_barrier();
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 14);
         const double kforce = *p.k_dev;
         for (int v = e; v < kMidMaxOut * BM; v += 32 * kMidEpiWarps) {            // item (t, r): output t (or Circular pair t) of row r
             const int t = v / BM, r = v % BM;
             if (t < p.nL) epart[t * BM + r] = output_head_parallel(p.out_type, p.nL, zfull + r, BM, cen + r * kMidCenLd, kforce, dzs + r, BM, t);
         }
         epi_barrier();
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 15);
         if (e < BM) {                                       // one thread per row: energy, scale exponents of the gradient rows
             const int r = e, m = m0 + r;
             double en = 0.0;
@@ -1382,6 +1502,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 5);
     }
     cluster_barrier();                                      // B: D2 is complete for this tile of replicas
+    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 6);
     // =========================== phase 2: D1 tiles ===========================
     if (warp == kMidEpiWarps) {
         if (lane == 0) {
@@ -1498,6 +1619,8 @@ struct TensorPlan {
     int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
+    bool prep_pipelined = true;                     // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
+    int prep_threads = 128;                         // CTA size of prep_kernel: 128 keeps all 1024 CTAs of a C5 batch resident at once
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
@@ -1591,7 +1714,8 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if (!encode_fn()) return no("cuTensorMapEncodeTiled is not available from this driver");
     if ((size_t) net.nodes[0] * sizeof(float) > 200 * 1024) return no("input layer too wide for the prep kernel's shared memory");
     if (cudaFuncSetAttribute(prep_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(prep_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        cudaFuncSetAttribute(prep_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(prep_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return no("cannot configure the prep kernel");
     TensorPlan* t = new TensorPlan();
     t->L = L;
@@ -1653,6 +1777,8 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     }
     // the fused middle kernel: fp16 pairs, two or more hidden layers, last hidden layer within one 4-CTA cluster, few outputs
     t->use_mid = kind == KIND_F16 && L >= 4 && net.nodes[L - 2] <= 128 * kMidCluster && net.nodes[L - 1] <= kMidMaxOut;
+    if (const char* env = getenv("ANNF_PREP_PIPELINED")) t->prep_pipelined = atoi(env) != 0;
+    if (const char* env = getenv("ANNF_PREP_THREADS")) t->prep_threads = atoi(env) == 256 ? 256 : 128;
     if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = t->use_mid && atoi(env) != 0;
     // fp32 biases live in NetView::b32 already
     {
@@ -1969,9 +2095,16 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
     for (int l = 0; l < kMaxLayers; l++) { chain.x_exp[l] = sl->x_exp[l]; chain.d_exp[l] = sl->d_exp[l]; }
     t->dbg_next = 0;
     cudaError_t err = timed("prep_kernel", [&] {
+        const bool whole_rows = t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0;
+        const size_t pipe_smem = 2 * (((size_t) 4 * t->nodes[0] + 127) & ~(size_t) 127);
+        if (KIND == KIND_F16 && whole_rows && !t->dry && t->prep_pipelined && pipe_smem <= 200 * 1024) {
+            const int grid = std::min(R, 2 * t->sm_count);
+            return launch_pdl(prep_pipelined_kernel, dim3(grid), dim3(kPrepPipeThreads), pipe_smem, stream, 1, 0, net, R, coords, atoms_per_replica,
+                              static_cast<__half*>(sl->x_hi[0]), static_cast<__half*>(sl->x_lo[0]), t->ld[0], chain, t->dbg_next++);
+        }
         const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
                                (t->dry ? 2 : 0);
-        return launch_pdl(prep_kernel<KIND>, dim3(R), dim3(256), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
+        return launch_pdl(prep_kernel<KIND>, dim3(R), dim3(t->prep_threads), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
                           sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain, t->dbg_next++);
     });
     if (err != cudaSuccess) return err;

@@ -277,7 +277,9 @@ def test_tensor_core_path_matches_oracle(nodes, types, R, precision):
     rel = np.abs(e - e_ref) / np.abs(e_ref)
     assert rel.max() <= (2e-4 if types[-1] == "Circular" else 2e-5), rel.max()
     assert np.median(rel) <= 3e-6, np.median(rel)
-    assert max_norm_rel(f, f_ref) <= F_RTOL
+    # forces through a Circular head are conditioned like its energy: a replica sitting next to its centre has a small
+    # force (k * Delta * dtheta/dx) and a fixed absolute angle error in it, hence the wider bar for that output type
+    assert max_norm_rel(f, f_ref) <= (5e-4 if types[-1] == "Circular" else F_RTOL)
     assert np.all(f[:, atoms:, :] == 0.0)
     # run-to-run determinism (split-K reduces in a fixed order)
     e2, f2, _ = run_batched(force, pos, cen, precision=precision)

@@ -32,7 +32,7 @@ for i in range(16):
     k.execute_batched(coords[i % 8], cen, out[i % 8], en)
 torch.cuda.synchronize()
 names = ["k0", "k1", "k2", "k3", "k4", "k5", "k6", "k7"]   # launch order: prep, forward GEMMs, (fused middle | GEMM, head, GEMM), backward GEMMs
-phase = ["entry", "prologue", "deps", "tma0", "landed0", "mma_done", "drained", "parked", "epilogue", "exit"]
+phase = ["entry", "prologue", "deps", "tma0", "landed0", "mma_done", "drained", "parked", "epilogue", "exit", "p10", "p11", "p12", "p13", "p14", "p15"]
 buf = (C.c_int64 * 192)()
 for rep in range(3):
     _capi.check(_capi.lib().annf_debug_tensor_phases(k._handle, buf, 1))
@@ -49,9 +49,9 @@ for rep in range(3):
     for s in range(8):
         if t[s][0] == 0:
             continue
-        rec = {phase[i]: round((int(t[s][i]) - t0) / 1e3, 2) for i in range(10) if t[s][i] > 0}
+        rec = {phase[i]: round((int(t[s][i]) - t0) / 1e3, 2) for i in range(16) if t[s][i] > 0}
         rec["last_cta_start"] = round((int(t[s][17]) - t0) / 1e3, 2)
         rec["last_cta_end"] = round((int(t[s][18]) - t0) / 1e3, 2)
         rows[names[s]] = rec
-        print("%-5s" % names[s], " ".join("%s=%.2f" % kv for kv in rec.items()))
+        print("%-5s" % names[s], " ".join("%s=%.2f" % kv for kv in sorted(rec.items(), key=lambda kv: kv[1])))
 print(json.dumps(dict(workload=work, replicas=R, unit="us since CTA 0 of the step's first kernel entered", kernels=rows)))
