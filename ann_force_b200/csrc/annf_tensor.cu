@@ -775,13 +775,52 @@ __device__ __forceinline__ int exp_for_bound(float bound) {
     return max(-kExpClamp, min(kExpClamp, kExpTarget - q));
 }
 
-// prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), centroid in fp64, write the operand pair.
+// prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), write the operand pair.
 // One CTA per replica; the replica's selected coordinates are staged once in shared memory.  Two passes and ONE block barrier:
-//   pass 1  global -> shared, per-component fp64 sums and fp32 min / max (the largest |p - centroid| of a component is attained
-//           at its min or max, so the row's scale exponent needs no pass of its own);
-//   pass 2  shared -> (p - centroid) / s in fp64 -> x 2^e -> operand pair -> global.
-// Work is walked in groups of 12 floats = 4 atoms, so that the component of every element is static (n_0 = 3A is a multiple
-// of 4 on this path, hence of 12).
+//   pass 1  global -> shared, per-component sums and min / max of d = p - p_ref (the largest |p - centroid| of a component is
+//           attained at its min or max, so the row's scale exponent needs no pass of its own);
+//   pass 2  shared -> (d - mean(d)) / s -> x 2^e -> operand pair -> global.
+// Arithmetic is fp32 RELATIVE TO A REFERENCE ATOM of the replica (p_ref = its first selected atom): d = p - p_ref is exact or
+// rounded relative to the molecule's extent, not to its distance from the origin, so p - centroid = d - mean(d) keeps every bit
+// a far-away molecule has (the fp64 centring this replaces gave the same guarantee, but its conversions — three per element —
+// ran on the FP64 pipe and made the kernel conversion-bound: 12.9 us for 18 MB in, 18 MB out; profiles/r02_prep.md).
+// 1 / s is carried as a float pair.  Work is walked in groups of 12 floats = 4 atoms, so that the component of every element
+// is static (n_0 = 3A is a multiple of 4 on this path, hence of 12).
+struct PrepRow {                                            // what pass 2 needs, identical in every thread of the CTA
+    float ref[3], mean[3];                                  // reference atom; mean of d per component
+    float inv_hi, inv_lo;                                   // 2^e / s as a float pair
+    float bound;                                            // largest |x| of the row (before the 2^e scale)
+    int e0;
+};
+
+// finishes the block reduction of pass 1 (every thread redundantly: broadcast reads instead of a second barrier)
+template <int KIND>
+__device__ __forceinline__ PrepRow prep_finish_reduction(const float (*red_sum)[3], const float (*red_min)[3], const float (*red_max)[3], int nwarps,
+                                                         const float* ref, int A, double scale) {
+    PrepRow row;
+    float bound = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float t = 0.f, lo = 3.0e38f, hi = -3.0e38f;
+        for (int w = 0; w < nwarps; w++) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
+        row.ref[c] = ref[c];
+        row.mean[c] = t / (float) A;                        // centroid - p_ref
+        bound = fmaxf(bound, fmaxf(fabsf(hi - row.mean[c]), fabsf(lo - row.mean[c])));
+    }
+    const double inv = 1.0 / scale;
+    row.bound = bound * (float) fabs(inv) * 1.000002f;      // head-room for the roundings on the way
+    row.e0 = KIND == KIND_F16 ? exp_for_bound(row.bound) : 0;
+    const double inv_scaled = ldexp(inv, row.e0);
+    row.inv_hi = (float) inv_scaled;
+    row.inv_lo = (float) (inv_scaled - (double) row.inv_hi);
+    return row;
+}
+
+__device__ __forceinline__ float prep_feature(const PrepRow& row, float e, int c) {
+    const float t = (e - row.ref[c]) - row.mean[c];
+    return fmaf(t, row.inv_hi, t * row.inv_lo);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
                                                   void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
@@ -797,9 +836,10 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;         // 128 or 256 (ANNF_PREP_THREADS)
     const int A = net.n_sel, quads = A / 4;
     const float* base = coords + (size_t) r * N * 3;
-    __shared__ double red_sum[8][3];
-    __shared__ float red_min[8][3], red_max[8][3];
-    double s[3] = {0.0, 0.0, 0.0};
+    __shared__ float red_sum[8][3], red_min[8][3], red_max[8][3];
+    const float* ref_ptr = base + (size_t) ((contiguous & 1) ? 0 : net.sel_atoms[0]) * 3;
+    const float ref[3] = {__ldg(ref_ptr), __ldg(ref_ptr + 1), __ldg(ref_ptr + 2)};
+    float s[3] = {0.f, 0.f, 0.f};
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (int g = tid; g < quads; g += nthreads) {
         float e[12];
@@ -822,9 +862,10 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
         dst[2] = make_float4(e[8], e[9], e[10], e[11]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            s[c] += ((double) e[c] + (double) e[3 + c]) + ((double) e[6 + c] + (double) e[9 + c]);
-            mn[c] = fminf(fminf(mn[c], fminf(e[c], e[3 + c])), fminf(e[6 + c], e[9 + c]));
-            mx[c] = fmaxf(fmaxf(mx[c], fmaxf(e[c], e[3 + c])), fmaxf(e[6 + c], e[9 + c]));
+            const float d0 = e[c] - ref[c], d1 = e[3 + c] - ref[c], d2 = e[6 + c] - ref[c], d3 = e[9 + c] - ref[c];
+            s[c] += (d0 + d1) + (d2 + d3);
+            mn[c] = fminf(fminf(mn[c], fminf(d0, d1)), fminf(d2, d3));
+            mx[c] = fmaxf(fmaxf(mx[c], fmaxf(d0, d1)), fmaxf(d2, d3));
         }
     }
 #pragma unroll
@@ -841,49 +882,29 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
         for (int c = 0; c < 3; c++) { red_sum[warp][c] = s[c]; red_min[warp][c] = mn[c]; red_max[warp][c] = mx[c]; }
     }
     __syncthreads();
-    // every thread finishes the reduction itself (72 broadcast reads) instead of a second barrier
-    const double inv_scale = 1.0 / net.scale;
-    double cc[3];
-    float bound = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        double t = 0.0;
-        float lo = 3.0e38f, hi = -3.0e38f;
-#pragma unroll
-        for (int w = 0; w < 8; w++)
-            if (w < nwarps) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
-        cc[c] = t / A;                                       // centroid of the unscaled coordinates
-        bound = fmaxf(bound, (float) (fmax(fabs((double) hi - cc[c]), fabs((double) lo - cc[c])) * fabs(inv_scale)));
-    }
-    // centring in fp64: a molecule far from the origin must not lose bits of (p - centroid)
-    int e0 = 0;
-    if (KIND == KIND_F16) {
-        // 2^-20 of head-room: `bound` is the exact largest magnitude up to the roundings of the two steps above
-        e0 = exp_for_bound(bound * 1.000001f);
-        if (tid == 0) {
-            chain.x_exp[0][r] = e0;
-            float b = bound;
-            for (int l = 0; l + 2 < net.L; l++) {            // X_{l+1} = act(W_l X_l + b_l)
-                b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
-                chain.x_exp[l + 1][r] = exp_for_bound(b);
-            }
+    const PrepRow row = prep_finish_reduction<KIND>(red_sum, red_min, red_max, nwarps, ref, A, net.scale);
+    if (KIND == KIND_F16 && tid == 0) {
+        chain.x_exp[0][r] = row.e0;
+        float b = row.bound;
+        for (int l = 0; l + 2 < net.L; l++) {                // X_{l+1} = act(W_l X_l + b_l)
+            b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
+            chain.x_exp[l + 1][r] = exp_for_bound(b);
         }
     }
-    const float sc = exp2i(e0);
     for (int g = tid; g < quads; g += nthreads) {
         const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
         const float4 p0 = src[0], p1 = src[1], p2 = src[2];
         const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
         float x[12];
 #pragma unroll
-        for (int j = 0; j < 12; j++) x[j] = (float) (((double) e[j] - cc[j % 3]) * inv_scale);
+        for (int j = 0; j < 12; j++) x[j] = prep_feature(row, e[j], j % 3);
         if (KIND == KIND_F16) {
             uint2* oh = reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld) + 3 * g;
             uint2* ol = reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld) + 3 * g;
 #pragma unroll
             for (int q = 0; q < 3; q++) {
                 uint2 hi, lo;
-                split_f16x4(make_float4(x[4 * q] * sc, x[4 * q + 1] * sc, x[4 * q + 2] * sc, x[4 * q + 3] * sc), hi, lo);
+                split_f16x4(make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), hi, lo);
                 oh[q] = hi;
                 ol[q] = lo;
             }
@@ -904,10 +925,11 @@ __global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const flo
     ANNF_TGRID_END(dbg);
 }
 
-// prep, persistent flavour (KIND_F16, selection = atoms 0..A-1, 16-byte aligned rows — the BASELINE C5 case): 2 CTAs per SM walk
-// the replicas; the NEXT row of coordinates arrives by one bulk copy (TMA engine, mbarrier) while the current one is reduced,
-// centred, scaled and split.  The one-CTA-per-replica kernel above is a chain of dependent phases per CTA — load, reduce,
-// barrier, convert, store — that all 1024 CTAs walk in lock-step: 12.9 us for 18 MB in and 18 MB out (profiles/r02_c5_phases_*).
+// prep, persistent flavour (KIND_F16, selection = atoms 0..A-1, 16-byte aligned rows): 2 CTAs per SM walk the replicas; the
+// NEXT row of coordinates arrives by one bulk copy (TMA engine, mbarrier) while the current one is reduced, centred, scaled
+// and split.  Opt-in (ANNF_PREP_PIPELINED=1): measured SLOWER than one CTA per replica at BASELINE C5 (step 130.9 against
+// 112.9 us, same session) — a row is a chain of dependent phases, and 16 warps per SM hide less of it than the 40 - 56 warps
+// of seven independent one-row CTAs (profiles/r02_prep.md).
 constexpr int kPrepPipeThreads = 256;
 __global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetView net, int R, const float* __restrict__ coords, int N,
                                                                        __half* __restrict__ x_hi, __half* __restrict__ x_lo, int ld,
@@ -916,8 +938,7 @@ __global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetVie
     const int A = net.n_sel, quads = A / 4, row_bytes = 12 * A;      // 3A floats; A % 4 == 0, so a row is a multiple of 48 bytes
     const int buf_stride = (row_bytes + 127) & ~127;
     __shared__ uint64_t bar[2];
-    __shared__ double red_sum[8][3];
-    __shared__ float red_min[8][3], red_max[8][3];
+    __shared__ float red_sum[8][3], red_min[8][3], red_max[8][3];
     ANNF_TGRID_START(dbg);
     if (threadIdx.x == 0) ANNF_TMARK(dbg, 0);
     pdl_launch_dependents();
@@ -930,7 +951,6 @@ __global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetVie
     __syncthreads();
     pdl_wait();
     if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
-    const double inv_scale = 1.0 / net.scale;
     int r = blockIdx.x;
     if (r < R && tid == 0) {
         ptx::bar_expect_tx(ptx::s_u32(&bar[0]), (uint32_t) row_bytes);
@@ -944,16 +964,19 @@ __global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetVie
         }
         ptx::bar_wait(ptx::s_u32(&bar[cur]), (uint32_t) (i >> 1) & 1u);
         const float4* src = reinterpret_cast<const float4*>(prep_smem + (size_t) cur * buf_stride);
-        double s[3] = {0.0, 0.0, 0.0};
+        const float* first = reinterpret_cast<const float*>(src);
+        const float ref[3] = {first[0], first[1], first[2]};
+        float s[3] = {0.f, 0.f, 0.f};
         float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
         for (int g = tid; g < quads; g += kPrepPipeThreads) {
             const float4 p0 = src[3 * g], p1 = src[3 * g + 1], p2 = src[3 * g + 2];
             const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                s[c] += ((double) e[c] + (double) e[3 + c]) + ((double) e[6 + c] + (double) e[9 + c]);
-                mn[c] = fminf(fminf(mn[c], fminf(e[c], e[3 + c])), fminf(e[6 + c], e[9 + c]));
-                mx[c] = fmaxf(fmaxf(mx[c], fmaxf(e[c], e[3 + c])), fmaxf(e[6 + c], e[9 + c]));
+                const float d0 = e[c] - ref[c], d1 = e[3 + c] - ref[c], d2 = e[6 + c] - ref[c], d3 = e[9 + c] - ref[c];
+                s[c] += (d0 + d1) + (d2 + d3);
+                mn[c] = fminf(fminf(mn[c], fminf(d0, d1)), fminf(d2, d3));
+                mx[c] = fmaxf(fmaxf(mx[c], fmaxf(d0, d1)), fmaxf(d2, d3));
             }
         }
 #pragma unroll
@@ -970,27 +993,15 @@ __global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetVie
             for (int c = 0; c < 3; c++) { red_sum[warp][c] = s[c]; red_min[warp][c] = mn[c]; red_max[warp][c] = mx[c]; }
         }
         __syncthreads();
-        double cc[3];
-        float bound = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            double t = 0.0;
-            float lo = 3.0e38f, hi = -3.0e38f;
-#pragma unroll
-            for (int w = 0; w < kPrepPipeThreads / 32; w++) { t += red_sum[w][c]; lo = fminf(lo, red_min[w][c]); hi = fmaxf(hi, red_max[w][c]); }
-            cc[c] = t / A;
-            bound = fmaxf(bound, (float) (fmax(fabs((double) hi - cc[c]), fabs((double) lo - cc[c])) * fabs(inv_scale)));
-        }
-        const int e0 = exp_for_bound(bound * 1.000001f);
+        const PrepRow row = prep_finish_reduction<KIND_F16>(red_sum, red_min, red_max, kPrepPipeThreads / 32, ref, A, net.scale);
         if (tid == 0) {
-            chain.x_exp[0][r] = e0;
-            float b = bound;
+            chain.x_exp[0][r] = row.e0;
+            float b = row.bound;
             for (int l = 0; l + 2 < net.L; l++) {
                 b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
                 chain.x_exp[l + 1][r] = exp_for_bound(b);
             }
         }
-        const float sc = exp2i(e0);
         uint2* oh = reinterpret_cast<uint2*>(x_hi + (size_t) r * ld);
         uint2* ol = reinterpret_cast<uint2*>(x_lo + (size_t) r * ld);
         for (int g = tid; g < quads; g += kPrepPipeThreads) {
@@ -998,7 +1009,7 @@ __global__ void __launch_bounds__(kPrepPipeThreads) prep_pipelined_kernel(NetVie
             const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
             float x[12];
 #pragma unroll
-            for (int j = 0; j < 12; j++) x[j] = (float) (((double) e[j] - cc[j % 3]) * inv_scale) * sc;
+            for (int j = 0; j < 12; j++) x[j] = prep_feature(row, e[j], j % 3);
 #pragma unroll
             for (int q = 0; q < 3; q++) {
                 uint2 hi, lo;
@@ -1619,8 +1630,8 @@ struct TensorPlan {
     int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
-    bool prep_pipelined = true;                     // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
-    int prep_threads = 128;                         // CTA size of prep_kernel: 128 keeps all 1024 CTAs of a C5 batch resident at once
+    bool prep_pipelined = false;                    // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
+    int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
@@ -1776,10 +1787,14 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
         }
     }
     // the fused middle kernel: fp16 pairs, two or more hidden layers, last hidden layer within one 4-CTA cluster, few outputs
-    t->use_mid = kind == KIND_F16 && L >= 4 && net.nodes[L - 2] <= 128 * kMidCluster && net.nodes[L - 1] <= kMidMaxOut;
+    // Opt-in (ANNF_TENSOR_MID=1), not the default: with one cluster of 4 CTAs per 128 replicas only 32 SMs work at BASELINE C5
+    // and the element-wise parts (tanh, fp64 output layer, act') are instruction-issue bound there — 60 us against 52 us for
+    // GEMM + head + GEMM spread over 64 - 1024 CTAs (profiles/r02_mid_kernel.md).
+    const bool mid_ok = kind == KIND_F16 && L >= 4 && net.nodes[L - 2] <= 128 * kMidCluster && net.nodes[L - 1] <= kMidMaxOut;
+    t->use_mid = false;
     if (const char* env = getenv("ANNF_PREP_PIPELINED")) t->prep_pipelined = atoi(env) != 0;
-    if (const char* env = getenv("ANNF_PREP_THREADS")) t->prep_threads = atoi(env) == 256 ? 256 : 128;
-    if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = t->use_mid && atoi(env) != 0;
+    if (const char* env = getenv("ANNF_PREP_THREADS")) t->prep_threads = atoi(env) == 128 ? 128 : 256;
+    if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = mid_ok && atoi(env) != 0;
     // fp32 biases live in NetView::b32 already
     {
         std::vector<int> sel(net.n_sel);
@@ -1974,7 +1989,7 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
         // ANNF_CLUSTER_DEBUG=1): a grid of 16 eight-CTA clusters runs in two waves.  So: the largest split whose 2 x S
         // clusters are all co-resident.
         int s = std::min(4, pick_split(tiles, kb, t->sm_count));
-        if (t->force_split > 0 && kb <= 32) s = std::min(4, t->force_split);
+        if (t->force_split > 0 && kb <= 32 && p.epi != EPI_FORCE) s = std::min(4, t->force_split);
         if (s == 4 && tiles / 2 > 15) s = 3;
         if (const char* env = getenv("ANNF_GEMM_NX_SPLIT")) s = atoi(env);
         switch (s) {
@@ -1990,7 +2005,7 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
         // instead of 64), split along K inside the same cluster (2 x S CTAs, S <= 4 keeps the cluster portable)
         const int pair_ctas = 2 * ((p.N + 127) / 128) * ((R + 255) / 256);
         int s = std::min(4, pick_split(pair_ctas, kb, t->sm_count));
-        if (t->force_split > 0 && kb <= 32) s = std::min(4, t->force_split);
+        if (t->force_split > 0 && kb <= 32 && p.epi != EPI_FORCE) s = std::min(4, t->force_split);
         // 2 x 4 clusters: a B200 co-schedules 15 of them, so 16 run in two waves; 2 x 3 clusters (96 CTAs at C5) fit in one
         if (s == 4 && pair_ctas / 2 > 15) s = 3;
         if (const char* env = getenv("ANNF_GEMM_PAIR_SPLIT")) s = atoi(env);
@@ -2004,7 +2019,7 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
     if (mode == 512) {
         const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);
         int s = pick_split(pair_ctas, kb, t->sm_count);
-        if (t->force_split > 0 && kb <= 32) s = t->force_split;
+        if (t->force_split > 0 && kb <= 32 && p.epi != EPI_FORCE) s = t->force_split;
         if (s == 8 && !t->no_cluster16) {
             // 2 x 8 = 16 CTAs is a non-portable cluster size: if this device cannot co-schedule it, remember and use 2 x 4
             const cudaError_t e = launch_gemm_t<KIND, 256, 8, 2>(op, p, stream);
@@ -2022,7 +2037,7 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
     const int bn = mode == 256 ? 256 : 128;
     const int tiles = ((p.N + bn - 1) / bn) * ((R + BM - 1) / BM);
     int s = pick_split(tiles, kb, t->sm_count);
-    if (t->force_split > 0 && kb <= 32) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
+    if (t->force_split > 0 && kb <= 32 && p.epi != EPI_FORCE) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
     if (bn == 256) {
         switch (s) {
         case 8: return launch_gemm_t<KIND, 256, 8, 1>(op, p, stream);

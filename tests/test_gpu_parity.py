@@ -261,12 +261,15 @@ def test_wide_network_properties_and_sampled_parity():
     ([600, 256, 256, 128, 3], ["Tanh", "Tanh", "Tanh", "Linear"], 130),   # three hidden layers: GEMM, GEMM, fused middle, GEMM, GEMM
     ([300, 128, 320, 16], ["Tanh", "Tanh", "Circular"], 260),    # 16 outputs (8 angles), last hidden layer over 3 of 4 cluster CTAs
 ])
-@pytest.mark.parametrize("precision", TENSOR_KINDS)
-def test_tensor_core_path_matches_oracle(nodes, types, R, precision):
+@pytest.mark.parametrize("precision", TENSOR_KINDS + ["f16x3+mid"])
+def test_tensor_core_path_matches_oracle(nodes, types, R, precision, monkeypatch):
     """tcgen05 path with the 11 + 11-bit operand split, carried as TF32 pairs (tf32x3) or as scaled fp16 pairs (f16x3).  Stated tolerance (BASELINE config 5 "tensor-core dense-contraction path, stated
     tolerance"), worst replica: energy 2e-5 relative for Tanh/Linear/Softmax outputs and 2e-4 for Circular outputs
     (an angle error d_theta costs k*Delta*d_theta, and Delta reaches pi); forces 1e-4 relative max-norm.
     The MEDIAN energy error must stay below 3e-6: a lost hi*lo term would put it near 5e-4."""
+    if precision.endswith("+mid"):                     # the fused forward / head / backward kernel of the last hidden connection (opt-in)
+        precision = precision[:-4]
+        monkeypatch.setenv("ANNF_TENSOR_MID", "1")
     atoms = nodes[0] // 3
     force = synthetic.make_force(nodes, types, atoms, seed=41)
     pos = synthetic.make_positions(atoms + 3, R, seed=42)
@@ -475,19 +478,19 @@ def test_large_replica_count_and_padded_rows():
 
 
 def test_fused_middle_kernel_matches_the_three_kernel_path(monkeypatch):
-    """f16x3 with the last hidden connection + head + its backward in ONE kernel (default) against the same step as GEMM,
-    head kernel, GEMM (ANNF_TENSOR_MID=0): same arithmetic except for the order of the output-layer partial sums, so the
+    """f16x3 with the last hidden connection + head + its backward in ONE kernel (ANNF_TENSOR_MID=1) against the same step as
+    GEMM, head kernel, GEMM (the default): same arithmetic except for the order of the output-layer partial sums, so the
     two agree far inside the parity bar; and both are deterministic run to run."""
     nodes, types, R = [1200, 512, 512, 8], ["Tanh", "Tanh", "Tanh"], 300
     force = synthetic.make_force(nodes, types, 400, seed=91)
     pos = synthetic.make_positions(400, R, seed=92)
     cen = synthetic.make_centers(force, R, seed=93)
+    e_sep, f_sep, _ = run_batched(force, pos, cen, precision="f16x3")
+    monkeypatch.setenv("ANNF_TENSOR_MID", "1")
     e_mid, f_mid, _ = run_batched(force, pos, cen, precision="f16x3")
     e_mid2, f_mid2, _ = run_batched(force, pos, cen, precision="f16x3")
     np.testing.assert_array_equal(e_mid, e_mid2)
     np.testing.assert_array_equal(f_mid, f_mid2)
-    monkeypatch.setenv("ANNF_TENSOR_MID", "0")
-    e_sep, f_sep, _ = run_batched(force, pos, cen, precision="f16x3")
     np.testing.assert_allclose(e_mid, e_sep, rtol=2e-6)
     assert max_norm_rel(f_mid, f_sep) <= 1e-5
     e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
