@@ -822,7 +822,7 @@ __device__ __forceinline__ float prep_feature(const PrepRow& row, float e, int c
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
+__global__ void __launch_bounds__(256, 7) prep_kernel(NetView net, int R, const float* __restrict__ coords, int N,
                                                   void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
                                                   ExpChain chain, int dbg) {
     extern __shared__ float xs[];                           // [3 * A]
@@ -1945,7 +1945,9 @@ static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p_in, cudaS
 
 static int pick_split(int tiles, int k_blocks, int sm_count) {
     int s = 1;
-    while (s < 8 && tiles * (s * 2) <= sm_count + sm_count / 8 && k_blocks / (s * 2) >= 4) s *= 2;
+    // at least two K-blocks per CTA.  (Four, until round 2: the 1024 x 512 x 512 GEMMs of BASELINE C5 then ran as 64 CTAs with
+    // split 2; split 4 = 128 CTAs halves both the main loop and the rows each CTA finishes: 16.8 -> 14.6 and 18.7 -> 16.2 us.)
+    while (s < 8 && tiles * (s * 2) <= sm_count + sm_count / 8 && k_blocks / (s * 2) >= 2) s *= 2;
     return s;
 }
 

@@ -277,9 +277,11 @@ def test_tensor_core_path_matches_oracle(nodes, types, R, precision, monkeypatch
     e, f, kernel = run_batched(force, pos, cen, precision=precision)
     assert kernel.info()["batched_path"] == "tensor" and kernel.info()["precision_batched"] == precision
     e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
-    rel = np.abs(e - e_ref) / np.abs(e_ref)
+    # a replica whose CVs happen to sit next to its centres has an energy far below the batch's and the same ABSOLUTE error
+    # in it (E = k/2 |cv - c|^2: dE = k (cv - c) dcv + k/2 dcv^2): such replicas are judged against the median energy
+    rel = np.abs(e - e_ref) / np.maximum(np.abs(e_ref), np.median(np.abs(e_ref)))
     assert rel.max() <= (2e-4 if types[-1] == "Circular" else 2e-5), rel.max()
-    assert np.median(rel) <= 3e-6, np.median(rel)
+    assert np.median(np.abs(e - e_ref) / np.abs(e_ref)) <= 3e-6
     # forces through a Circular head are conditioned like its energy: a replica sitting next to its centre has a small
     # force (k * Delta * dtheta/dx) and a fixed absolute angle error in it, hence the wider bar for that output type
     assert max_norm_rel(f, f_ref) <= (5e-4 if types[-1] == "Circular" else F_RTOL)
