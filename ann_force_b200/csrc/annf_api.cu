@@ -2,6 +2,7 @@
 // upload, kernel selection and the launchers.  No exceptions cross this boundary and there is no
 // CPU fallback: without a CUDA device every entry point fails with ANNF_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -640,7 +641,7 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
     int chunks = 1;
     {
         const size_t bytes = sizeof(float) * n_coords;
-        if (bytes >= (4u << 20)) chunks = 4;
+        if (bytes >= (4u << 20)) chunks = 3;
         else if (bytes >= (1u << 20)) chunks = 2;
         if (const char* env = getenv("ANNF_HOST_CHUNKS")) chunks = atoi(env);
         chunks = std::max(1, std::min(std::min(chunks, 8), R));
@@ -661,19 +662,37 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
         ANNF_CUDA(cudaStreamSynchronize(s));
         return ANNF_OK;
     }
-    // Chunk sizes DEcrease (weights chunks+1, chunks, ..., 2): the copy-in stream is the long pole, so what remains after
-    // its last byte lands — evaluating and copying out the LAST chunk — should be as short as possible.
+    // Chunk sizes DEcrease geometrically (each chunk `ratio` times smaller than the one before; ANNF_HOST_CHUNK_RATIO, 1 = equal).
+    // What the schedule balances, measured with ANNF_HOST_TRACE=1 at BASELINE C5 (profiles/r02_host_trace.md): the link is NOT
+    // full duplex in practice — a copy-in moves 49 GB/s alone and 28 GB/s while a copy-out is running — so the 36.9 MB of a step
+    // cross at ~75 GB/s in aggregate once both directions are busy, and the schedule only decides how soon that state is
+    // reached (small first chunk) and how short the tail after the last byte lands is (small last chunk), against ~35 us of
+    // host submission per chunk.  3 chunks at ratio 1.5 measured best (0.647 ms; 4 equal chunks 0.75, 4 at ratio 2 0.69).
     int bounds[9];
     {
-        const long long total_w = (long long) chunks * (chunks + 3) / 2;
-        long long acc = 0;
+        double ratio = 1.5;
+        if (const char* env = getenv("ANNF_HOST_CHUNK_RATIO")) ratio = std::max(1.0, atof(env));
+        double weights[8], total_w = 0.0;
+        for (int c = 0; c < chunks; c++) { weights[c] = std::pow(ratio, chunks - 1 - c); total_w += weights[c]; }
+        double acc = 0.0;
         bounds[0] = 0;
         for (int c = 0; c < chunks; c++) {
-            acc += chunks + 1 - c;
-            bounds[c + 1] = (int) ((long long) R * acc / total_w);
+            acc += weights[c];
+            bounds[c + 1] = (int) std::llround((double) R * acc / total_w);
         }
         bounds[chunks] = R;
         for (int c = 0; c < chunks; c++) if (bounds[c + 1] <= bounds[c]) bounds[c + 1] = std::min(R, bounds[c] + 1);
+    }
+    // ANNF_HOST_TRACE=1 (diagnostic): device timeline of this call — when each chunk's copy-in, evaluation and copy-out
+    // finished, in us since the first copy was enqueued — printed to stderr as one JSON line, plus host submission times.
+    static const bool trace = getenv("ANNF_HOST_TRACE") != nullptr;
+    cudaEvent_t tr0 = nullptr, tr_in[8] = {}, tr_comp[8] = {}, tr_out[8] = {};
+    double host_us[8] = {};
+    const auto host_t0 = std::chrono::steady_clock::now();
+    if (trace) {
+        cudaEventCreate(&tr0);
+        for (int c = 0; c < chunks; c++) { cudaEventCreate(&tr_in[c]); cudaEventCreate(&tr_comp[c]); cudaEventCreate(&tr_out[c]); }
+        cudaEventRecord(tr0, h->in_stream);
     }
     for (int c = 0; c < chunks; c++) {
         const int r0 = bounds[c], r1 = bounds[c + 1], n = r1 - r0;
@@ -685,6 +704,7 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
         cudaStream_t compute = (c & 1) ? h->host_stream2 : h->host_stream;
         h->tensor_slot = c & 1;
         ANNF_CUDA(cudaEventRecord(h->ev_in[c], h->in_stream));
+        if (trace) cudaEventRecord(tr_in[c], h->in_stream);
         ANNF_CUDA(cudaStreamWaitEvent(compute, h->ev_in[c], 0));
         if (zero_fill) ANNF_CUDA(cudaMemsetAsync(h->h_forces + r0 * row, 0, sizeof(float) * n * row, compute));
         annf_status st = annf_eval_batched(h, n, h->h_coords + r0 * row, atoms_per_replica,
@@ -697,14 +717,32 @@ annf_status annf_eval_batched_host(annf_handle h, int32_t R, const float* coords
             return st;
         }
         ANNF_CUDA(cudaEventRecord(h->ev_comp[c], compute));
+        if (trace) cudaEventRecord(tr_comp[c], compute);
         ANNF_CUDA(cudaStreamWaitEvent(h->out_stream, h->ev_comp[c], 0));
         ANNF_CUDA(cudaMemcpyAsync(forces_host + r0 * row, h->h_forces + r0 * row, sizeof(float) * n * row, cudaMemcpyDeviceToHost, h->out_stream));
         ANNF_CUDA(cudaMemcpyAsync(energies_host + r0, h->h_energies + r0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->out_stream));
+        if (trace) {
+            cudaEventRecord(tr_out[c], h->out_stream);
+            host_us[c] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+        }
     }
     ANNF_CUDA(cudaStreamSynchronize(h->out_stream));
     ANNF_CUDA(cudaStreamSynchronize(h->host_stream));
     ANNF_CUDA(cudaStreamSynchronize(h->host_stream2));
     ANNF_CUDA(cudaStreamSynchronize(h->in_stream));
+    if (trace) {
+        const double host_done = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "{\"annf_host_trace\": {\"replicas\": %d, \"host_returned_us\": %.1f, \"chunks\": [", R, host_done);
+        for (int c = 0; c < chunks; c++) {
+            float a = 0.f, b = 0.f, d = 0.f;
+            cudaEventElapsedTime(&a, tr0, tr_in[c]); cudaEventElapsedTime(&b, tr0, tr_comp[c]); cudaEventElapsedTime(&d, tr0, tr_out[c]);
+            fprintf(stderr, "%s{\"rows\": %d, \"host_submitted_us\": %.1f, \"copied_in_us\": %.1f, \"evaluated_us\": %.1f, \"copied_out_us\": %.1f}",
+                    c ? ", " : "", bounds[c + 1] - bounds[c], host_us[c], 1e3 * a, 1e3 * b, 1e3 * d);
+            cudaEventDestroy(tr_in[c]); cudaEventDestroy(tr_comp[c]); cudaEventDestroy(tr_out[c]);
+        }
+        fprintf(stderr, "]}}\n");
+        cudaEventDestroy(tr0);
+    }
     return ANNF_OK;
 }
 
