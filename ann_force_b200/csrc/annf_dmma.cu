@@ -31,8 +31,17 @@ namespace annf {
 constexpr int kDWarps = 16;
 constexpr int kDComputeThreads = 32 * kDWarps;
 constexpr int kDThreads = kDComputeThreads + 32;      // + one producer warp
-constexpr int kDStages = 2;
-constexpr int kDStageBytes = 64 * 1024;
+// the weight ring: ANNF_DMMA_STAGES x ANNF_DMMA_STAGE_KB (compile-time; the product build's values were picked by measurement,
+// profiles/r02_dmma_ring.md)
+#ifndef ANNF_DMMA_STAGES
+#define ANNF_DMMA_STAGES 2
+#endif
+#ifndef ANNF_DMMA_STAGE_KB
+#define ANNF_DMMA_STAGE_KB 64
+#endif
+constexpr int kDStages = ANNF_DMMA_STAGES;
+constexpr int kDStageBytes = ANNF_DMMA_STAGE_KB * 1024;
+constexpr int kDBarSlots = (2 * kDStages + 2 + 15) / 16 * 16;   // full[S], empty[S], coords, statics (16-byte multiples)
 constexpr int kDTile = 8;                             // replicas per CTA = rows of the DMMA A operand
 constexpr int kDMaxNT = 4;                            // node tiles (of 8) per warp
 
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kDThreads, 1) annf_dmma_kernel(const DmmaArgs 
     unsigned char* ring = smem_raw;                                                   // [stages][32 KB]
     unsigned char* ptr = ring + (size_t) kDStages * kDStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ptr);                                // full[S], empty[S], coords, statics
-    ptr += 16 * sizeof(uint64_t);
+    ptr += kDBarSlots * sizeof(uint64_t);
     auto carve = [&](size_t bytes) { unsigned char* q = ptr; ptr += (bytes + 15) & ~(size_t) 15; return q; };   // 16-byte regions
     const StreamPlan& plan = *reinterpret_cast<const StreamPlan*>(carve(sizeof(StreamPlan)));
     const double* bias_s = reinterpret_cast<const double*>(carve(sizeof(double) * (size_t) total));
@@ -419,7 +428,7 @@ cudaError_t read_dmma_phase_clocks(long long* out64) {
 size_t dmma_smem_bytes(const NetView& net, const StreamPlan& plan) {
     auto up = [](size_t b) { return (b + 15) & ~(size_t) 15; };
     const size_t total = plan.total, nL = net.nodes[net.L - 1], tr = kDTile;
-    size_t bytes = (size_t) kDStages * kDStageBytes + 16 * sizeof(uint64_t);
+    size_t bytes = (size_t) kDStages * kDStageBytes + kDBarSlots * sizeof(uint64_t);
     bytes += up(sizeof(StreamPlan)) + up(sizeof(double) * total) + up(sizeof(int) * (size_t) net.n_sel);        // statics
     bytes += 3 * up(sizeof(double) * nL * tr) + up(sizeof(double) * tr * net.num_center) + up(sizeof(double) * tr * 3) +
              up(sizeof(double) * kDWarps * 3) + up(sizeof(double) * (size_t) plan.scratch_unit);
