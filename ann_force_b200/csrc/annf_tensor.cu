@@ -86,6 +86,12 @@ struct GemmParams {
     const int* out_exp;               // [M] rows of the result (activations / gradients coming out); unused by EPI_FORCE / EPI_STORE
     const int* aux_exp;               // [M] rows of aux
     const int* sel_atoms;             // selected atom -> atom index, or nullptr when the selection is 0..A-1 (EPI_FORCE)
+    // Split-K THROUGH GLOBAL MEMORY (S = 1 kernels only): gridDim.z CTAs (or CTA pairs) share an output tile, each over its own
+    // K range; partial tiles meet in `gs_scratch`, CTAs meet on the counters, every one finishes 1/gridDim.z of the rows.
+    int gsplit;                       // number of K ranges (0 / 1: off)
+    float* gs_scratch;                // [tiles][gsplit][BM][BN] fp32 partial tiles
+    int* gs_arrive;                   // [tiles] partial tiles published so far (self-resetting)
+    int* gs_done;                     // [tiles] CTAs that have finished reading (the last one resets both counters)
     int direct_store;                 // EPI_FORCE, unsplit, identity selection, 16-byte aligned rows: the tile leaves through tm_out (TMA store)
     int dbg;                          // diagnostic builds: slot of g_tensor_clock this launch records into (-1: none)
     int chunk;                        // K-blocks accumulated in TMEM between two promotions into the fp32 register accumulators
@@ -223,7 +229,13 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define ANNF_TGRID_START(slot) do { if ((slot) >= 0 && threadIdx.x == 0) { const unsigned long long t_ = gtimer(); \
         atomicMin(&g_tensor_clock[slot][16], t_); atomicMax(&g_tensor_clock[slot][17], t_); } } while (0)
 #define ANNF_TGRID_END(slot) do { if ((slot) >= 0 && threadIdx.x == 0) atomicMax(&g_tensor_clock[slot][18], gtimer()); } while (0)
+// SM cycles CTA 0's single-thread roles spent waiting: [19] MMA issuer on accumulator buffers, [20] MMA issuer on operands,
+// [21] TMA producer on free stages, [22] epilogue warp 0 on finished chunks
+#define ANNF_TWAIT_BEGIN() const long long tw_ = clock64()
+#define ANNF_TWAIT_END(slot, i) do { if ((slot) >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tensor_clock[slot][i] += (unsigned long long) (clock64() - tw_); } while (0)
 #else
+#define ANNF_TWAIT_BEGIN() do { } while (0)
+#define ANNF_TWAIT_END(slot, i) do { } while (0)
 #define ANNF_TMARK(slot, i) do { } while (0)
 #define ANNF_TGRID_START(slot) do { } while (0)
 #define ANNF_TGRID_END(slot) do { } while (0)
@@ -434,6 +446,42 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const 
     }
 }
 
+// Epilogue of a tile whose K ranges were computed by `gs` different CTAs (split-K through global memory): this CTA finishes rows
+// [grank * rows, ...) of the tile, summing the gs partial tiles in a fixed order (deterministic).  Same rolled, software-
+// pipelined structure as cooperative_epilogue; the partials are read with ld.global.cg (they were written by other SMs).
+template <int KIND, int BN, int kGroupThreads>
+__device__ __forceinline__ void global_split_epilogue(const GemmParams& p, const EpiVec& vec, const float* tile_partials, int gs, int grank,
+                                                      int m0, int n0, int t) {
+    constexpr int kVecPerRow = BN / 4;
+    const int rows = (BM + gs - 1) / gs;
+    const int groups = (rows * kVecPerRow + kGroupThreads - 1) / kGroupThreads;
+    struct Group { EpiAux aux; float4 sum; int m, n; bool ok; };
+    auto fetch = [&](int g) {
+        Group q;
+        const int v = t + g * kGroupThreads;
+        const int row = grank * rows + v / kVecPerRow, col = (v % kVecPerRow) * 4;
+        q.m = m0 + row; q.n = n0 + col;
+        q.ok = g < groups && v < rows * kVecPerRow && row < BM && q.m < p.M && q.n < p.N;
+        q.sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q.ok) {
+            q.aux = epilogue_load<KIND>(p, vec, q.m, q.n, row, col);
+            const float* src = tile_partials + (size_t) row * BN + col;
+            for (int r = 0; r < gs; r++) {                                         // fixed order: deterministic
+                const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t) r * BM * BN));
+                q.sum.x += x.x; q.sum.y += x.y; q.sum.z += x.z; q.sum.w += x.w;
+            }
+        }
+        return q;
+    };
+    Group next = fetch(0);
+#pragma unroll 1
+    for (int g = 0; g < groups; g++) {
+        const Group cur = next;
+        next = fetch(g + 1);
+        if (cur.ok) epilogue_finish<KIND>(p, cur.m, cur.n, cur.sum, cur.aux);
+    }
+}
+
 // Block- or cluster-wide rendezvous used by every warp role at the same two points of the kernel.
 template <bool kCluster> __device__ __forceinline__ void role_sync() {
     if (kCluster) {
@@ -493,7 +541,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const uint16_t mc_mask = (uint16_t) (3u << (my_cta & ~1u));                   // NX = 2: this CTA and its x neighbour
     const uint32_t leader_cta = my_cta & ~1u;
     const int kb_total = (p.K + BK - 1) / BK;
-    const int kb0 = (int) ((long long) kb_total * rank / S), kb1 = (int) ((long long) kb_total * (rank + 1) / S);
+    const int gs = (S == 1 && p.gsplit > 1) ? p.gsplit : 1;                       // split-K through global memory (gridDim.z ranges)
+    const int grank = gs > 1 ? (int) blockIdx.z : 0;
+    const int ksplits = S > 1 ? S : gs, krank = S > 1 ? rank : grank;
+    const int kb0 = (int) ((long long) kb_total * krank / ksplits), kb1 = (int) ((long long) kb_total * (krank + 1) / ksplits);
     const int num_kb = kb1 - kb0;
     const int kChunk = p.chunk;
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
@@ -563,7 +614,40 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     auto finish_tile = [&](bool participates) {
         role_sync<(S > 1 || NX == 2)>();                    // every partial tile (of the split) is parked; NX = 2: the peer no longer multicasts into this CTA's stages
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 7);
-        if (participates && !(p.dry & 8) && !(S == 1 && direct))
+        if (S == 1 && gs > 1) {
+            if (participates && !(p.dry & 8)) {
+                // publish this CTA's partial tile, meet the other K ranges of the tile, finish 1 / gs of its rows
+                const int n_tiles = (int) gridDim.x / CG;
+                const int tile = ((int) blockIdx.y * n_tiles + n0 / BN) * CG + pair_rank;
+                float* mine = p.gs_scratch + ((size_t) tile * gs + grank) * BM * BN;
+                const float* staging = reinterpret_cast<const float*>(data);
+                for (int v = (int) threadIdx.x; v < BM * (BN / 4); v += kEpiThreads) {
+                    const int row = v / (BN / 4), col = (v % (BN / 4)) * 4;
+                    __stcg(reinterpret_cast<float4*>(mine + (size_t) row * BN + col),
+                           *reinterpret_cast<const float4*>(staging + (size_t) row * Cfg::kStagingLd + col));
+                }
+                __threadfence();
+                asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+                if (threadIdx.x == 0) {
+                    atomicAdd(p.gs_arrive + tile, 1);
+                    // every CTA of the grid is resident (the launcher sizes the grid to the SM count), so this wait ends; the
+                    // bound turns a violated assumption into a reported error instead of a hang
+                    const long long t_start = clock64();
+                    while (*reinterpret_cast<volatile int*>(p.gs_arrive + tile) < gs)
+                        if (clock64() - t_start > (1ll << 31)) __trap();
+                    __threadfence();
+                }
+                asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+                if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 10);
+                global_split_epilogue<KIND, BN, kEpiThreads>(p, vec, p.gs_scratch + (size_t) tile * gs * BM * BN, gs, grank, m0, n0, (int) threadIdx.x);
+                asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+                if (threadIdx.x == 0 && atomicAdd(p.gs_done + tile, 1) == gs - 1) {     // the last reader re-arms the tile for the next launch
+                    p.gs_done[tile] = 0;
+                    p.gs_arrive[tile] = 0;
+                    __threadfence();
+                }
+            }
+        } else if (participates && !(p.dry & 8) && !(S == 1 && direct))
             cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, data, rank, x_rank, m0, n0, (int) threadIdx.x);
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
         role_sync<(S > 1 || CX == 2)>();                    // nobody leaves while peers still read / share TMEM
@@ -578,7 +662,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 for (int i = 0; i < num_kb; i++) {
                     const int s = i % kStages;
                     const uint32_t ph = (uint32_t) (i / kStages) & 1u;
+                    { ANNF_TWAIT_BEGIN();
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free (in both CTAs of a pair)
+                    ANNF_TWAIT_END(p.dbg, 21); }
                     const uint32_t full = smem_u32(&bar_full[s]);
                     if (p.dry & 4) {                                              // experiments: no TMA traffic
                         if (CG == 2 && pair_rank == 1) mbar_arrive_cluster(map_to_cta(full, leader_cta));
@@ -632,7 +718,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 for (int c = 0; c < num_chunks; c++) {
                     const int buf = c % NB;
                     const uint32_t use = (uint32_t) (c / NB);
+                    { ANNF_TWAIT_BEGIN();
                     mbar_wait(smem_u32(&bar_acc_empty[buf]), (use & 1u) ^ 1u);    // epilogue warps (of both CTAs) drained this buffer
+                    ANNF_TWAIT_END(p.dbg, 19); }
                     tcgen05_fence_after();
                     const uint32_t tmem_acc = tmem_base + (uint32_t) (buf * BN);
                     const int i_end = min(num_kb, (c + 1) * kChunk);
@@ -640,7 +728,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     for (; i < i_end; i++) {
                         const int s = i % kStages;
                         const uint32_t ph = (uint32_t) (i / kStages) & 1u;
+                        { ANNF_TWAIT_BEGIN();
                         mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed (both CTAs)
+                        ANNF_TWAIT_END(p.dbg, 20); }
                         tcgen05_fence_after();
                         if (i == 0) ANNF_TMARK(p.dbg, 4);
                         const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
@@ -686,7 +776,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         for (int c = 0; c < num_chunks; c++) {
             const int buf = c % NB;
             const uint32_t use = (uint32_t) (c / NB);
+            { ANNF_TWAIT_BEGIN();
             mbar_wait(smem_u32(&bar_acc_full[buf]), use & 1u);
+            if (threadIdx.x == 0) ANNF_TWAIT_END(p.dbg, 22); }
             tcgen05_fence_after();
 #pragma unroll
             for (int cc = 0; cc < kColsPerWarp / 32; cc++) {
@@ -1536,6 +1628,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         gp.out_hi = p.d1_hi; gp.out_lo = p.d1_lo; gp.ld_out = p.ld1;
         gp.a_exp = nullptr; gp.b_exp = nullptr; gp.out_exp = nullptr; gp.aux_exp = nullptr;   // staged in `vec`
         gp.sel_atoms = nullptr; gp.direct_store = 0; gp.dbg = -1; gp.chunk = 1; gp.dry = 0;
+        gp.gsplit = 0; gp.gs_scratch = nullptr; gp.gs_arrive = nullptr; gp.gs_done = nullptr;
         for (int t = rank; t < tiles1; t += CL) {
             drain(nkb2);
             if (e < 128) s_b_exp[e] = (t * 128 + e) < p.n1 ? __ldg(p.wt_exp + t * 128 + e) : 0;
@@ -1601,6 +1694,8 @@ struct GemmOp {
     char name[48];
 };
 
+constexpr int kGsMaxTiles = 64;                    // output tiles (x CTA of a pair) a globally split GEMM may have
+constexpr size_t kGsScratchBytes = (size_t) 160 * BM * 256 * sizeof(float);   // up to 160 partial tiles of 128 x 256 fp32 (21 MB)
 constexpr int kPlanSlots = 2;         // independent activation-buffer sets: two chunks of a call may be in flight at once
 
 struct PlanSlot {
@@ -1608,6 +1703,8 @@ struct PlanSlot {
     // activations X_l (l = 0..L-2) and pre-activation gradients D_l (l = 1..L-2) as operand pairs (fp32 words or halves)
     void *x_hi[kMaxLayers] = {}, *x_lo[kMaxLayers] = {}, *d_hi[kMaxLayers] = {}, *d_lo[kMaxLayers] = {};
     int *x_exp[kMaxLayers] = {}, *d_exp[kMaxLayers] = {};   // KIND_F16: per-row scale exponents of the same tensors
+    float* gs_scratch = nullptr;                    // split-K through global memory: partial tiles (kGsScratchBytes)
+    int* gs_counters = nullptr;                     // 2 x kGsMaxTiles ints: arrive[], done[]
     std::vector<GemmOp> fwd, bwd;
 };
 
@@ -1632,6 +1729,7 @@ struct TensorPlan {
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
     bool prep_pipelined = false;                    // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
+    int gsplit_mode = -1;                           // ANNF_GEMM_GSPLIT: -1 auto, 0 off, n > 1 forces n K ranges (split-K through global memory)
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
@@ -1643,6 +1741,8 @@ static void free_activations(PlanSlot* t) {
         t->x_hi[l] = t->x_lo[l] = t->d_hi[l] = t->d_lo[l] = nullptr;
         t->x_exp[l] = t->d_exp[l] = nullptr;
     }
+    cudaFree(t->gs_scratch); cudaFree(t->gs_counters);
+    t->gs_scratch = nullptr; t->gs_counters = nullptr;
     t->cap = 0;
 }
 
@@ -1792,6 +1892,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     // GEMM + head + GEMM spread over 64 - 1024 CTAs (profiles/r02_mid_kernel.md).
     const bool mid_ok = kind == KIND_F16 && L >= 4 && net.nodes[L - 2] <= 128 * kMidCluster && net.nodes[L - 1] <= kMidMaxOut;
     t->use_mid = false;
+    if (const char* env = getenv("ANNF_GEMM_GSPLIT")) t->gsplit_mode = atoi(env);
     if (const char* env = getenv("ANNF_PREP_PIPELINED")) t->prep_pipelined = atoi(env) != 0;
     if (const char* env = getenv("ANNF_PREP_THREADS")) t->prep_threads = atoi(env) == 128 ? 128 : 256;
     if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = mid_ok && atoi(env) != 0;
@@ -1833,6 +1934,8 @@ static cudaError_t ensure_capacity(TensorPlan* plan, PlanSlot* t, const NetView&
         if (l >= 1 && err == cudaSuccess) err = alloc(&t->d_lo[l], bytes);
         if (l >= 1 && err == cudaSuccess) err = alloc((void**) &t->d_exp[l], sizeof(int) * cap);
     }
+    if (err == cudaSuccess) err = alloc((void**) &t->gs_scratch, kGsScratchBytes);
+    if (err == cudaSuccess) err = alloc((void**) &t->gs_counters, sizeof(int) * 2 * kGsMaxTiles);
     if (err != cudaSuccess) return err;
     t->cap = cap;
     t->fwd.clear();
@@ -1938,7 +2041,9 @@ static cudaError_t launch_gemm_t(const GemmOp& op, const GemmParams& p_in, cudaS
     }
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM * CG - 1) / (BM * CG);
     constexpr bool kBox64 = Cfg::kBRows < 128;
-    return launch_pdl(gemm3x_kernel<KIND, BN, S, CG, NX>, dim3(CG * n_tiles, m_tiles, S), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG * NX, S,
+    if (BN >= 256) p.chunk = std::max(p.chunk, 2);          // two TMEM buffers only: one-block chunks put the drain on the MMA issuer's critical path
+    const int grid_z = S > 1 ? S : std::max(1, p.gsplit);   // S = 1: gridDim.z = K ranges of a split through global memory (no cluster along z)
+    return launch_pdl(gemm3x_kernel<KIND, BN, S, CG, NX>, dim3(CG * n_tiles, m_tiles, grid_z), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, CG * NX, S,
                       NX == 2 ? op.a_hi64 : op.a_hi, NX == 2 ? op.a_lo64 : op.a_lo, kBox64 ? op.b_hi64 : op.b_hi, kBox64 ? op.b_lo64 : op.b_lo,
                       p.direct_store ? op.out : op.a_hi, p);
 }
@@ -1952,7 +2057,7 @@ static int pick_split(int tiles, int k_blocks, int sm_count) {
 }
 
 template <int KIND>
-static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaStream_t stream, const NetView& net,
+static cudaError_t launch_gemm(TensorPlan* t, PlanSlot* sl, const GemmOp& op_in, int R, cudaStream_t stream, const NetView& net,
                                float* forces, int atoms_per_replica) {
     constexpr int BK = KindOf<KIND>::kBlockElems;
     GemmOp op = op_in;
@@ -1974,6 +2079,25 @@ static cudaError_t launch_gemm(TensorPlan* t, const GemmOp& op_in, int R, cudaSt
     // enough work to fill the machine with 256 x 256 tiles (possibly split along K); small GEMMs stay on 128 x 128 tiles.
     const int kb = (p.K + BK - 1) / BK;
     int mode = t->force_bn;                                     // 0 auto, 128 / 256: 1-CTA tiles, 512: CTA pairs
+    // Long-K GEMMs that cannot fill the machine with unsplit tiles (BASELINE C5's 1024 x 512 x 4500): 256 x 256 CTA-pair tiles,
+    // K split over gridDim.z through global memory.  The 1-CTA 128 x 128 kernel reads 8 KB of shared memory per 64-cycle MMA
+    // and is bound by shared-memory bandwidth (160 KB of reads + TMA writes per K-block against 128 B/clk: 1250 cycles per
+    // block for 768 of MMA); a pair reads its own A and HALF of B per MMA (1250 against 1536 cycles: MMA-bound), but splitting
+    // K inside the cluster would need 16-CTA clusters.  Global split: any number of K ranges, the grid sized to the SM count.
+    const bool gs_forced = t->gsplit_mode > 0;                  // experiments / tests: any shape the machine holds
+    if (mode == 0 && sl != nullptr && p.epi != EPI_FORCE && t->gsplit_mode != 0 && (gs_forced || (p.N >= 256 && kb >= 32))) {
+        const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);
+        const int gsp = gs_forced ? std::min(t->gsplit_mode, kb) : std::min(t->sm_count / pair_ctas, kb / 4);
+        const int tiles = pair_ctas;                              // one counter per CTA of a pair
+        if (gsp >= 2 && (gs_forced || pair_ctas * gsp >= (3 * t->sm_count) / 4) && pair_ctas * gsp <= t->sm_count && tiles <= kGsMaxTiles &&
+            (size_t) tiles * gsp * BM * 256 * sizeof(float) <= kGsScratchBytes) {
+            p.gsplit = gsp;
+            p.gs_scratch = sl->gs_scratch;
+            p.gs_arrive = sl->gs_counters;
+            p.gs_done = sl->gs_counters + kGsMaxTiles;
+            return launch_gemm_t<KIND, 256, 1, 2>(op, p, stream);
+        }
+    }
     if (mode == 0) {
         const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);
         const int s2 = pick_split(pair_ctas, kb, t->sm_count);
@@ -2130,7 +2254,7 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
         if (mid && i + 1 == sl->fwd.size()) break;        // the last hidden connection belongs to the fused middle kernel
         const GemmOp& op = sl->fwd[i];
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
-        err = timed(name, [&] { return launch_gemm<KIND>(t, op, R, stream, net, nullptr, 0); });
+        err = timed(name, [&] { return launch_gemm<KIND>(t, sl, op, R, stream, net, nullptr, 0); });
         if (err != cudaSuccess) return err;
     }
     if (mid) {
@@ -2146,7 +2270,7 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
     for (size_t i = mid ? 1 : 0; i < sl->bwd.size(); i++) {
         const GemmOp& op = sl->bwd[i];
         snprintf(name, sizeof(name), "gemm[%dx%dx%d] %s", R, op.p.N, op.p.K, strstr(op.name, "] ") + 2);
-        err = timed(name, [&] { return launch_gemm<KIND>(t, op, R, stream, net, forces, atoms_per_replica); });
+        err = timed(name, [&] { return launch_gemm<KIND>(t, sl, op, R, stream, net, forces, atoms_per_replica); });
         if (err != cudaSuccess) return err;
     }
     return cudaSuccess;

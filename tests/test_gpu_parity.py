@@ -479,6 +479,33 @@ def test_large_replica_count_and_padded_rows():
     assert max_norm_rel(f[sample][:, :7], f_ref[:, :7]) <= 1e-6
 
 
+@pytest.mark.parametrize("precision", TENSOR_KINDS)
+@pytest.mark.parametrize("splits", ["2", "3", "5"])
+def test_split_k_through_global_memory(splits, precision, monkeypatch):
+    """CTA-pair tiles whose K ranges live in different CTAs (gridDim.z) and meet in global memory: forced onto small shapes
+    (ragged M: 300 rows = one full and one partial pair tile; ragged N; K not a multiple of the block) and run THREE times on
+    the same handle — the arrival counters re-arm themselves — with bit-identical results (the partials are summed in a
+    fixed order)."""
+    monkeypatch.setenv("ANNF_GEMM_GSPLIT", splits)
+    nodes, types, R = [1200, 600, 320, 6], ["Tanh", "Tanh", "Tanh"], 300
+    force = synthetic.make_force(nodes, types, 400, seed=51)
+    pos = synthetic.make_positions(400, R, seed=52)
+    kernel = CalcANNForce(precision=precision)
+    kernel.initialize(400, force)
+    coords = torch.as_tensor(pos, device="cuda")
+    runs = []
+    for _ in range(3):
+        e, f = kernel.execute_batched(coords)
+        torch.cuda.synchronize()
+        runs.append((e.cpu().numpy().copy(), f.double().cpu().numpy().copy()))
+    for e, f in runs[1:]:
+        np.testing.assert_array_equal(e, runs[0][0])
+        np.testing.assert_array_equal(f, runs[0][1])
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64))
+    np.testing.assert_allclose(runs[0][0], e_ref, rtol=2e-5)
+    assert max_norm_rel(runs[0][1], f_ref) <= F_RTOL
+
+
 def test_fused_middle_kernel_matches_the_three_kernel_path(monkeypatch):
     """f16x3 with the last hidden connection + head + its backward in ONE kernel (ANNF_TENSOR_MID=1) against the same step as
     GEMM, head kernel, GEMM (the default): same arithmetic except for the order of the output-layer partial sums, so the

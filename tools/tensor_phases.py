@@ -52,6 +52,8 @@ for rep in range(3):
         rec = {phase[i]: round((int(t[s][i]) - t0) / 1e3, 2) for i in range(16) if t[s][i] > 0}
         rec["last_cta_start"] = round((int(t[s][17]) - t0) / 1e3, 2)
         rec["last_cta_end"] = round((int(t[s][18]) - t0) / 1e3, 2)
+        if t[s][19] or t[s][20] or t[s][21] or t[s][22]:       # SM cycles spent waiting, as us at 1.965 GHz (not times on the axis)
+            print("      waits (us): mma on accumulators %.2f, mma on operands %.2f, producer on stages %.2f, epilogue on chunks %.2f" % tuple(int(t[s][i]) / 1965.0 for i in (19, 20, 21, 22)))
         rows[names[s]] = rec
         print("%-5s" % names[s], " ".join("%s=%.2f" % kv for kv in sorted(rec.items(), key=lambda kv: kv[1])))
 print(json.dumps(dict(workload=work, replicas=R, unit="us since CTA 0 of the step's first kernel entered", kernels=rows)))
