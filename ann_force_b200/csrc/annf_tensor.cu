@@ -1729,7 +1729,7 @@ struct TensorPlan {
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
     bool prep_pipelined = false;                    // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
-    int gsplit_mode = -1;                           // ANNF_GEMM_GSPLIT: -1 auto, 0 off, n > 1 forces n K ranges (split-K through global memory)
+    int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
@@ -2079,11 +2079,14 @@ static cudaError_t launch_gemm(TensorPlan* t, PlanSlot* sl, const GemmOp& op_in,
     // enough work to fill the machine with 256 x 256 tiles (possibly split along K); small GEMMs stay on 128 x 128 tiles.
     const int kb = (p.K + BK - 1) / BK;
     int mode = t->force_bn;                                     // 0 auto, 128 / 256: 1-CTA tiles, 512: CTA pairs
-    // Long-K GEMMs that cannot fill the machine with unsplit tiles (BASELINE C5's 1024 x 512 x 4500): 256 x 256 CTA-pair tiles,
-    // K split over gridDim.z through global memory.  The 1-CTA 128 x 128 kernel reads 8 KB of shared memory per 64-cycle MMA
-    // and is bound by shared-memory bandwidth (160 KB of reads + TMA writes per K-block against 128 B/clk: 1250 cycles per
-    // block for 768 of MMA); a pair reads its own A and HALF of B per MMA (1250 against 1536 cycles: MMA-bound), but splitting
-    // K inside the cluster would need 16-CTA clusters.  Global split: any number of K ranges, the grid sized to the SM count.
+    // Opt-in experiment (ANNF_GEMM_GSPLIT=-1 auto, n forces n ranges): long-K GEMMs that cannot fill the machine with unsplit
+    // tiles (BASELINE C5's 1024 x 512 x 4500) on 256 x 256 CTA-pair tiles, K split over gridDim.z through global memory.
+    // Motivation: the 1-CTA 128 x 128 kernel reads 8 KB of shared memory per 64-cycle MMA and is bound by shared-memory
+    // bandwidth (160 KB of reads + TMA writes per K-block against 128 B/clk: 1250 cycles per block for 768 of MMA); a pair
+    // reads its own A and HALF of B per MMA (1250 against 1536 cycles: MMA-bound), but splitting K inside the cluster would
+    // need 16-CTA clusters.  Measured at C5 (9 ranges, 144 CTAs; profiles/r02_c5_phases_gsplit.txt): main loop 14.5 -> 9.9 us,
+    // but publishing 18.9 MB of partial tiles, the rendezvous and the 9-way sum from L2 cost 13 us against the 6.7 us tail of
+    // the in-cluster DSMEM reduction: 36.6 against 29.1 us per launch.  Hence off by default.
     const bool gs_forced = t->gsplit_mode > 0;                  // experiments / tests: any shape the machine holds
     if (mode == 0 && sl != nullptr && p.epi != EPI_FORCE && t->gsplit_mode != 0 && (gs_forced || (p.N >= 256 && kb >= 32))) {
         const int pair_ctas = 2 * ((p.N + 255) / 256) * ((R + 255) / 256);
