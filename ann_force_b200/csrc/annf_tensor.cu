@@ -974,7 +974,15 @@ __global__ void __launch_bounds__(256, 7) prep_kernel(NetView net, int R, const 
         for (int c = 0; c < 3; c++) { red_sum[warp][c] = s[c]; red_min[warp][c] = mn[c]; red_max[warp][c] = mx[c]; }
     }
     __syncthreads();
-    const PrepRow row = prep_finish_reduction<KIND>(red_sum, red_min, red_max, nwarps, ref, A, net.scale);
+    // warp 0 finishes the reduction and publishes the row's constants; a second barrier is cheaper than the 72 broadcast
+    // reads + arithmetic of every thread finishing it for itself (the kernel is instruction-issue bound: profiles/r02_prep.md)
+    __shared__ PrepRow row_s;
+    if (warp == 0) {
+        const PrepRow r0 = prep_finish_reduction<KIND>(red_sum, red_min, red_max, nwarps, ref, A, net.scale);
+        if (lane == 0) row_s = r0;
+    }
+    __syncthreads();
+    const PrepRow row = row_s;
     if (KIND == KIND_F16 && tid == 0) {
         chain.x_exp[0][r] = row.e0;
         float b = row.bound;

@@ -231,11 +231,15 @@ def test_wide_network_properties_and_sampled_parity():
     cen = synthetic.make_centers(force, R)
     e, f, kernel = run_batched(force, pos, cen, precision="auto")
     assert kernel.info()["batched_path"] == "tensor" and kernel.info()["precision_batched"] == "f16x3"
-    sample = [0, 11, 23]
+    sample = list(range(0, 24, 2))
     e_ref, f_ref = port.evaluate(force, pos[sample].astype(np.float64), cen[sample].astype(np.float64))
-    tol_e = 2e-5 if kernel.info()["precision_batched"] != "fp64" else 1e-10
-    np.testing.assert_allclose(e[sample], e_ref, rtol=tol_e)
-    assert max_norm_rel(f[sample], f_ref) <= F_RTOL
+    # The bar for the HEADLINE configuration is twice what bench.py measures on it (parity block, 64 replicas against the
+    # reference CPU kernel: energy 6.8e-7 worst / 1.3e-7 median, forces 1.2e-6 worst; profiles/r02_bench_default.json) —
+    # the north-star 1e-6 / 1e-4, not the looser "stated tolerance" the other tensor-path shapes are held to.
+    rel = np.abs(e[sample] - e_ref) / np.abs(e_ref)
+    assert rel.max() <= 1.4e-6, rel.max()
+    assert np.median(rel) <= 4e-7, np.median(rel)
+    assert max_norm_rel(f[sample], f_ref) <= 2.5e-6
     # zero net force per replica
     assert np.abs(f.sum(axis=1)).max() <= 1e-3 * np.abs(f).max()
     # translation invariance

@@ -5,7 +5,7 @@ CPU-only numerical experiment (numpy): BASELINE C5 (4500-512-512-8, Tanh) is eva
 and then again with ONE source of rounding switched on at a time, in the order the device path applies them:
 
   split      operands kept as an 11 + 11-bit pair (TF32 pair, or fp16 pair of the row-scaled value), lo*lo dropped
-  chunk      fp32 accumulation: every 128-wide K chunk summed exactly, rounded to fp32 (the TMEM accumulator's best case),
+  chunk      fp32 accumulation: every --chunk-k wide K chunk summed exactly, rounded to fp32 (the TMEM accumulator's best case),
              then added into an fp32 accumulator with round-to-nearest (the "promotion" adds of the kernel)
   trunc      the same, but the in-chunk accumulation truncates toward zero after every MMA instruction (an emulation of the
              non-rounding tensor-core accumulator; 8 (tf32) or 16 (f16) products per instruction, three instructions per step)
@@ -69,7 +69,7 @@ def trunc32(x):
     return f
 
 
-def contract(a, w, kind, mode, a_exp=None, w_exp=None):
+def contract(a, w, kind, mode, a_exp=None, w_exp=None, chunk_k=64):
     """a [R, K] · w[N, K]^T the way the device does it.  mode: exact | split | chunk | trunc"""
     if mode == "exact":
         return a @ w.T
@@ -87,8 +87,8 @@ def contract(a, w, kind, mode, a_exp=None, w_exp=None):
     if mode == "split":
         return (al @ wh.T + ah @ wl.T + ah @ wh.T) * unscale
     acc = np.zeros((a.shape[0], w.shape[0]), dtype=np.float32)
-    for k0 in range(0, K, 128):
-        sl = slice(k0, min(K, k0 + 128))
+    for k0 in range(0, K, chunk_k):
+        sl = slice(k0, min(K, k0 + chunk_k))
         if mode == "chunk":
             part = (al[:, sl] @ wh[:, sl].T + ah[:, sl] @ wl[:, sl].T + ah[:, sl] @ wh[:, sl].T).astype(np.float32)
         else:
@@ -101,7 +101,7 @@ def contract(a, w, kind, mode, a_exp=None, w_exp=None):
     return acc.astype(np.float64) * unscale
 
 
-def evaluate(force, pos, cen, kind, mode, act32):
+def evaluate(force, pos, cen, kind, mode, act32, chunk_k=64):
     nodes = force.get_num_of_nodes()
     L = len(nodes)
     W = [np.asarray(w, dtype=np.float64).reshape(nodes[l + 1], nodes[l]) for l, w in enumerate(force.get_coeffients_of_connections())]
@@ -118,7 +118,7 @@ def evaluate(force, pos, cen, kind, mode, act32):
     for l in range(L - 2):
         a_exp = row_exp(bound)
         w_exp = row_exp(np.abs(W[l].astype(np.float32)).max(axis=1).astype(np.float64))
-        z = contract(acts[-1], W[l], kind, mode, a_exp, w_exp)
+        z = contract(acts[-1], W[l], kind, mode, a_exp, w_exp, chunk_k)
         z = f32(f32(z) + f32(B[l]))
         acts.append(f32(np.tanh(z)))
         bound = np.ones(R)
@@ -144,7 +144,7 @@ def evaluate(force, pos, cen, kind, mode, act32):
         gmax = np.abs(g).max(axis=1)
         a_exp = row_exp(gmax * 1.0)
         w_exp = row_exp(np.abs(Wt.astype(np.float32)).max(axis=1).astype(np.float64))
-        g = contract(g, Wt, kind, mode, a_exp, w_exp)
+        g = contract(g, Wt, kind, mode, a_exp, w_exp, chunk_k)
         if l > 0:
             a = acts[l]
             g = f32(f32(g) * f32(1 - f32(a * a))) if act32 else g * (1 - a * a)
@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=32)
     ap.add_argument("--kind", default="f16", choices=["f16", "tf32"])
     ap.add_argument("--workload", default="c5")
+    ap.add_argument("--chunk-k", type=int, default=64, help="K values accumulated in the (truncating) tensor-core accumulator between promotions")
     args = ap.parse_args()
     cfg = synthetic.CONFIGS[args.workload]
     force = synthetic.make_config(args.workload)
@@ -165,12 +166,12 @@ def main():
     out = {}
     for name, mode, act32 in (("split", "split", False), ("chunk", "chunk", False), ("trunc", "trunc", False),
                               ("act", "exact", True), ("all", "trunc", True)):
-        e, f = evaluate(force, pos, cen, args.kind, mode, act32)
+        e, f = evaluate(force, pos, cen, args.kind, mode, act32, args.chunk_k)
         rel = np.abs(e - e0) / np.abs(e0)
         frel = np.abs(f - f0).reshape(args.replicas, -1).max(axis=1) / np.abs(f0).reshape(args.replicas, -1).max(axis=1)
         out[name] = dict(energy_rel_median=float(np.median(rel)), energy_rel_max=float(rel.max()), force_rel_maxnorm=float(frel.max()))
         print("%-6s energy rel median %.2e max %.2e   force max-norm %.2e" % (name, np.median(rel), rel.max(), frel.max()), flush=True)
-    print(json.dumps(dict(workload=args.workload, kind=args.kind, replicas=args.replicas, settings=out)))
+    print(json.dumps(dict(workload=args.workload, kind=args.kind, replicas=args.replicas, chunk_k=args.chunk_k, settings=out)))
 
 
 if __name__ == "__main__":
