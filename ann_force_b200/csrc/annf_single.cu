@@ -513,6 +513,10 @@ struct FastArgs {
     int padded;
     unsigned flags;
     void* energy;
+    int input_type;             // ANNF_INPUT_*: Cartesian, or pair distances / dihedral cos-sin over the feature atoms
+    int n_feat;                 // pairs or dihedrals
+    const int* feat;            // [2 * n_feat] or [4 * n_feat] indices INTO the feature-atom list
+    double scale;
 };
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
@@ -590,7 +594,10 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
     double* cen = eterm + nL;                             // umbrella centre
     double* kval = cen + args.num_center;                 // force constant
     double* red = kval + 1;                               // [3 * warps] centroid partial sums, [3] centroid
-    int* slots_s = reinterpret_cast<int*>(red + 3 * kSingleWarps + 4);   // position-buffer slot of every selected atom
+    const bool cartesian = args.input_type == ANNF_INPUT_CARTESIAN;
+    double* fpos = red + 3 * kSingleWarps + 4;            // pair / dihedral inputs: positions of the feature atoms [3 * A] ...
+    double* facc = fpos + (cartesian ? 0 : 3 * A);        // ... and their force accumulators [3 * A]
+    int* slots_s = reinterpret_cast<int*>(facc + (cartesian ? 0 : 3 * A));   // position-buffer slot of every selected atom
 
     // ---- parameters: one bulk copy + two tiny cp.async, consumed after the positions are in -----------------------
     const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&blob_bar);
@@ -612,7 +619,31 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
     ANNF_PHASE(11);
 
     // ---- feature stage: ANN_ReferenceKernels.cpp:128-151 (every CTA builds the full centred input) ----------------
-    if (A <= 32) {
+    if (!cartesian) {
+        // pair distances (:152-160) or dihedral cos / sin (:125-127, :579-636) over the staged positions of the feature atoms
+        for (int i = tid; i < A; i += kSingleThreads) {
+            const int slot = args.sel_slots[i];
+            slots_s[i] = slot;
+            const double3 p = load_pos(args.posq, args.posq_corr, args.flags, slot);
+            fpos[3 * i] = p.x; fpos[3 * i + 1] = p.y; fpos[3 * i + 2] = p.z;
+            facc[3 * i] = 0.0; facc[3 * i + 1] = 0.0; facc[3 * i + 2] = 0.0;
+        }
+        __syncthreads();
+        if (args.input_type == ANNF_INPUT_PAIR_DISTANCES) {
+            for (int p = tid; p < args.n_feat; p += kSingleThreads) {
+                const double* pa = fpos + 3 * args.feat[2 * p];
+                const double* pb = fpos + 3 * args.feat[2 * p + 1];
+                const double inv = args.inv_scale;                                          // Vec3 / scalar multiplies by the reciprocal
+                const double dx = pa[0] * inv - pb[0] * inv, dy = pa[1] * inv - pb[1] * inv, dz = pa[2] * inv - pb[2] * inv;
+                a[p] = sqrt(dx * dx + dy * dy + dz * dz);
+            }
+        } else {
+            for (int q = tid; q < args.n_feat; q += kSingleThreads) {
+                const int* id = args.feat + 4 * q;
+                dihedral_cos_sin(fpos + 3 * id[0], fpos + 3 * id[1], fpos + 3 * id[2], fpos + 3 * id[3], a[2 * q], a[2 * q + 1]);
+            }
+        }
+    } else if (A <= 32) {
         // the whole selection sits in warp 0: butterfly sums leave the centroid in every lane, no block-level hop
         if (warp == 0) {
             double x = 0.0, y = 0.0, w = 0.0;
@@ -751,13 +782,42 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
                 if (l >= 1) {
                     const double av = al[m];
                     publish(dl + m, type == ANNF_TANH ? sum * (1 - av * av) : sum);                 // :343-354
-                } else {
+                } else if (cartesian) {
                     const int i = m / 3, c = m - 3 * i;
                     atomicAdd(&args.force[slots_s[i] + c * args.padded],
                               (unsigned long long) ((long long) (sum * (double) 0x100000000LL)));
+                } else {
+                    publish(dl + m, sum);                                                           // dE/d(feature): the chain rule follows
                 }
             });
-            if (l >= 1) sync_all();
+            if (l >= 1 || !cartesian) sync_all();
+        }
+        if (!cartesian && rank == 0) {
+            // get_all_forces_from_derivative_of_first_layer: pair branch :411-421, dihedral branch :392-396 (+ :425-577).
+            // Contributions are summed per feature atom in shared memory first, then one fixed-point atomicAdd per component.
+            const double* g = d;
+            if (args.input_type == ANNF_INPUT_PAIR_DISTANCES) {
+                for (int p = tid; p < args.n_feat; p += kSingleThreads) {
+                    const int i0 = args.feat[2 * p], i1 = args.feat[2 * p + 1];
+                    const double dx = fpos[3 * i0] - fpos[3 * i1], dy = fpos[3 * i0 + 1] - fpos[3 * i1 + 1], dz = fpos[3 * i0 + 2] - fpos[3 * i1 + 2];
+                    const double f = g[p] / (args.scale * sqrt(dx * dx + dy * dy + dz * dz));
+                    atomicAdd(&facc[3 * i0], -dx * f); atomicAdd(&facc[3 * i0 + 1], -dy * f); atomicAdd(&facc[3 * i0 + 2], -dz * f);
+                    atomicAdd(&facc[3 * i1], dx * f); atomicAdd(&facc[3 * i1 + 1], dy * f); atomicAdd(&facc[3 * i1 + 2], dz * f);
+                }
+            } else {
+                for (int q = tid; q < args.n_feat; q += kSingleThreads) {
+                    const int* id = args.feat + 4 * q;
+                    double f[4][3];
+                    dihedral_forces(fpos + 3 * id[0], fpos + 3 * id[1], fpos + 3 * id[2], fpos + 3 * id[3], g[2 * q], g[2 * q + 1], f);
+                    for (int k = 0; k < 4; k++)
+                        for (int c = 0; c < 3; c++) atomicAdd(&facc[3 * id[k] + c], f[k][c]);
+                }
+            }
+            __syncthreads();
+            for (int t = tid; t < 3 * A; t += kSingleThreads) {
+                const int i = t / 3, c = t - 3 * i;
+                atomicAdd(&args.force[slots_s[i] + c * args.padded], (unsigned long long) ((long long) (facc[t] * (double) 0x100000000LL)));
+            }
         }
     }
     ANNF_PHASE(5);
@@ -789,7 +849,7 @@ static int pick_lanes_log2(int nrows, int ncols) {
 // w[l] are the fp64 weights of connection l, row-major [n_out][n_in]; b64 the flat biases (net.b_off).
 bool fast_single_plan(const NetView& net, int cluster_size, const std::vector<std::vector<double>>& w, const std::vector<double>& b64,
                       FastPlan* plan, std::vector<double>* blobs) {
-    if (net.input_type != ANNF_INPUT_CARTESIAN) return false;
+    const bool cartesian = net.input_type == ANNF_INPUT_CARTESIAN;
     const int L = net.L;
     for (int l = 0; l + 2 < L; l++)
         if (net.types[l] != ANNF_TANH && net.types[l] != ANNF_LINEAR) return false;
@@ -803,7 +863,8 @@ bool fast_single_plan(const NetView& net, int cluster_size, const std::vector<st
         for (int t = 0; t < n0; t++) wsum[(size_t) (t % 3) * n1 + k] += w[0][(size_t) k * n0 + t];
     for (int t = 0; t < n0; t++)
         for (int k = 0; k < n1; k++)
-            wt0c[(size_t) t * n1 + k] = -(w[0][(size_t) k * n0 + t] - wsum[(size_t) (t % 3) * n1 + k] / A) / net.scale;
+            wt0c[(size_t) t * n1 + k] = cartesian ? -(w[0][(size_t) k * n0 + t] - wsum[(size_t) (t % 3) * n1 + k] / A) / net.scale
+                                                  : w[0][(size_t) k * n0 + t];       // pair / dihedral inputs: plain W_0^T, the chain rule follows in the kernel
     // layout of one blob (identical offsets in every CTA)
     int f_per[kMaxLayers], b_per[kMaxLayers], f_off[kMaxLayers], fb_off[kMaxLayers], b_off[kMaxLayers];
     size_t off = kHdrInts / 2;
@@ -846,7 +907,7 @@ bool fast_single_plan(const NetView& net, int cluster_size, const std::vector<st
     plan->blob_doubles = (int) blob_doubles;
     const int total = net.node_off[L], nL = net.nodes[L - 1];
     plan->smem_doubles = (int) (blob_doubles + 2 * (size_t) total + 2 * (size_t) nL + net.num_center + 1 + 3 * kSingleWarps + 4 +
-                                ((size_t) A + 1) / 2 + 2);
+                                (cartesian ? 0 : 6 * (size_t) A) + ((size_t) A + 1) / 2 + 2);
     return (size_t) plan->smem_doubles * sizeof(double) <= 200 * 1024;
 }
 
@@ -876,6 +937,10 @@ cudaError_t launch_single_fast(const NetView& net, const FastPlan& plan, const d
     args.padded = padded;
     args.energy = energy;
     args.flags = flags;
+    args.input_type = net.input_type;
+    args.n_feat = net.input_type == ANNF_INPUT_PAIR_DISTANCES ? net.n_pairs : net.n_dihedrals;
+    args.feat = net.input_type == ANNF_INPUT_PAIR_DISTANCES ? net.pairs : net.dihedrals;
+    args.scale = net.scale;
     const size_t smem = sizeof(double) * (size_t) plan.smem_doubles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.cl);

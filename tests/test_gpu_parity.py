@@ -448,6 +448,41 @@ def test_other_featurisers_single_and_batched(kind):
     assert np.abs(f1 - f1_ref).max() <= 1e-10 * np.abs(f1_ref).max() + 2 * FIXED_POINT_ULP
 
 
+@pytest.mark.parametrize("input_type", [2, 0])
+def test_low_latency_single_kernel_on_a_cluster_with_feature_inputs(input_type):
+    """Pair-distance / dihedral inputs on the low-latency single-replica kernel when the network is wide enough to span a
+    thread-block cluster (weights > 48 KB per CTA): features built redundantly in every CTA, dE/d(feature) published through
+    DSMEM, chain rule + scatter in CTA 0.  fp64 bars."""
+    n_atoms = 14
+    rng = np.random.default_rng(17)
+    g = ANN_Force()
+    if input_type == 2:
+        pairs = [(i + 1, j + 1) for i in range(n_atoms) for j in range(i + 1, n_atoms)][:60]
+        n0 = len(pairs)
+        g.set_list_of_pair_index_for_distances(pairs)
+    else:
+        quads = [[i + 1, i + 2, i + 3, i + 4] for i in range(n_atoms - 3)]
+        n0 = 2 * len(quads)
+        g.set_list_of_index_of_atoms_forming_dihedrals(quads)
+    nodes = [n0, 256, 4]
+    g.set_num_of_nodes(nodes)
+    g.set_layer_types(["Tanh", "Circular"])
+    g.set_coeffients_of_connections([rng.uniform(-0.3, 0.3, nodes[0] * nodes[1]), rng.uniform(-0.2, 0.2, nodes[1] * nodes[2])])
+    g.set_values_of_biased_nodes([rng.uniform(-0.1, 0.1, nodes[1]), rng.uniform(-0.1, 0.1, nodes[2])])
+    g.set_potential_center([0.4, -1.3])
+    g.set_force_constant(70.0)
+    g.set_scaling_factor(0.4)
+    g.set_data_type_in_input_layer(input_type)
+    g.set_index_of_backbone_atoms(list(range(1, n_atoms + 1)))
+    pos = synthetic.make_positions(n_atoms, 1, seed=71)[0].astype(np.float64)
+    order = np.random.default_rng(9).permutation(n_atoms)
+    e1, f1, seen, kernel = run_single(g, pos, "double", order=order)
+    assert kernel.info()["single_path"] == "low-latency" and kernel.info()["cluster_size"] > 1
+    e_ref, f_ref = port.evaluate(g, seen)
+    assert abs(e1 - e_ref) <= 1e-11 * abs(e_ref)
+    assert np.abs(f1 - f_ref).max() <= 1e-10 * np.abs(f_ref).max() + 2 * FIXED_POINT_ULP
+
+
 # ------------------------------------------------------------------------------------------------------
 # edge cases: empty and very large batches, rows wider than the system
 # ------------------------------------------------------------------------------------------------------
@@ -558,7 +593,8 @@ def test_tensor_path_capacity_growth_and_reuse(precision):
 # kernel variants: the low-latency / streamed kernels are the default where they apply; the generic
 # kernels (every layer type, every input type) stay covered through the documented environment switches
 # ------------------------------------------------------------------------------------------------------
-ELEMENTWISE_GOLDEN = [n for n in CARTESIAN_GOLDEN if n.startswith(("ref_cartesian", "ref_sweep", "syn_"))]
+ELEMENTWISE_GOLDEN = [n for n in CARTESIAN_GOLDEN if n.startswith(("ref_cartesian", "ref_sweep_20", "ref_sweep_100", "ref_pairdist", "ref_dihedral",
+                                                                   "ref_alanine", "syn_"))]
 
 
 def test_default_kernel_selection():
@@ -571,7 +607,12 @@ def test_default_kernel_selection():
     kernel = CalcANNForce()
     kernel.initialize(10, pairs)
     info = kernel.info()
-    assert info["single_path"] == "generic" and info["batched_path"] == "fused"
+    # pair-distance and dihedral inputs: the low-latency single-replica kernel as well (round 2), the fused kernel for batches
+    assert info["single_path"] == "low-latency" and info["batched_path"] == "fused"
+    mixed = synthetic.make_force([12, 8, 6, 6, 3], ["Tanh", "Circular", "Softmax", "Linear"], 4, seed=21)
+    kernel = CalcANNForce()
+    kernel.initialize(4, mixed)
+    assert kernel.info()["single_path"] == "generic"              # Circular / Softmax HIDDEN layers: the generic cluster kernel
 
 
 @pytest.mark.parametrize("name", ELEMENTWISE_GOLDEN)
