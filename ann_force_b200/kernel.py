@@ -159,7 +159,8 @@ class CalcANNForce:
 
     # ---- batched replicas (HOST buffers: the end-to-end entry) --------------------------------------------------------
     def execute_batched_host(self, coords, centers=None, forces=None, energies=None):
-        """coords: float32 [R, N, 3] numpy array or CPU torch tensor (pinned for full PCIe speed).
+        """coords: float32 [R, N, 3] numpy array or CPU torch tensor, C-contiguous (checked).  PINNED buffers let the copies
+        overlap the evaluation of neighbouring chunks; pageable ones give the same result with the driver staging every copy.
         Copies in, evaluates, copies forces/energies out and waits.  Returns (energies, forces) of the same kind."""
         self._need()
         torch = _torch()
@@ -168,11 +169,27 @@ class CalcANNForce:
         def ptr(x):
             return C.c_void_p(x.data_ptr() if is_torch else x.ctypes.data)
 
+        def ok(x, dtype_t, dtype_n, shape, what):
+            """The C entry takes raw pointers: a wrong dtype, a strided view or a device tensor would be misread silently."""
+            if is_torch:
+                good = isinstance(x, torch.Tensor) and not x.is_cuda and x.dtype == dtype_t and x.is_contiguous() and tuple(x.shape) == shape
+            else:
+                good = isinstance(x, np.ndarray) and x.dtype == dtype_n and x.flags["C_CONTIGUOUS"] and tuple(x.shape) == shape
+            if not good:
+                raise ValueError("execute_batched_host: %s must be a C-contiguous host %s of shape %s" % (what, dtype_n.__name__, shape))
+
+        if coords.ndim != 3 or coords.shape[2] != 3:
+            raise ValueError("execute_batched_host: coords must have shape [R, N, 3]")
         R, N, _ = coords.shape
+        ok(coords, torch.float32, np.float32, (R, N, 3), "coords")
+        if centers is not None:
+            ok(centers, torch.float32, np.float32, (R, self._num_center), "centers")
         if forces is None:
             forces = torch.empty_like(coords) if is_torch else np.empty_like(coords)
         if energies is None:
             energies = torch.empty(R, dtype=torch.float64) if is_torch else np.empty(R, dtype=np.float64)
+        ok(forces, torch.float32, np.float32, (R, N, 3), "forces")
+        ok(energies, torch.float64, np.float64, (R,), "energies")
         _capi.check(_capi.lib().annf_eval_batched_host(self._handle, int(R), ptr(coords), int(N),
                                                        ptr(centers) if centers is not None else None,
                                                        ptr(forces), ptr(energies)))

@@ -493,6 +493,10 @@ def main():
                         avg_launch_ms=avg_ms, launches=rec["launches"],
                         share_of_step=rec["total_ms"] / max(sum(v["total_ms"] for v in times.values()), 1e-12),
                         algorithmic_flops_per_launch=kflops, peak_source=peak_source,
+                        # a three-product kernel (hi*hi + hi*lo + lo*hi) can reach at most 1/3 of the pipe's dense peak;
+                        # frac_vs_dense_tf32_peak is the same achieved rate against round 1's denominator (bf16 / 2)
+                        frac_of_three_product_ceiling=(3.0 * achieved / peak) if bound == "tensor" else None,
+                        frac_vs_dense_tf32_peak=(achieved / (peaks["bf16_tflops"] / 2.0)) if bound == "tensor" else None,
                         note=(None if args.workload == "c5" else
                               "latency-bound shape: a launch is a chain of dependent layers; the fraction is reported for information"),
                         kernels={k: dict(launches=v["launches"], avg_ms=v["total_ms"] / max(v["launches"], 1)) for k, v in times.items()})

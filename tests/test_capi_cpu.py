@@ -100,6 +100,25 @@ def test_no_cpu_fallback():
         force.validate()
 
 
+def test_host_entry_rejects_buffers_it_would_misread():
+    """execute_batched_host hands raw pointers to the C ABI: dtype, shape and contiguity are checked first (no GPU needed:
+    the checks run before the library is called)."""
+    kernel = CalcANNForce()
+    kernel._handle = C.c_void_p(1)           # pretend-initialised: the argument checks come before any use of the handle
+    kernel._num_center = 2
+    try:
+        good = np.zeros((4, 7, 3), dtype=np.float32)
+        for bad in (good.astype(np.float64), good[:, ::2, :], np.zeros((4, 7, 2), dtype=np.float32)):
+            with pytest.raises(ValueError):
+                kernel.execute_batched_host(bad)
+        with pytest.raises(ValueError):
+            kernel.execute_batched_host(good, centers=np.zeros((4, 3), dtype=np.float32))
+        with pytest.raises(ValueError):
+            kernel.execute_batched_host(good, energies=np.zeros(4, dtype=np.float32))
+    finally:
+        kernel._handle = C.c_void_p()
+
+
 def test_product_never_imports_the_oracle():
     for top in ("ann_force_b200", "include", "tools", "openmm_stub"):      # product, boundary, diagnostics, stand-in
         for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
