@@ -27,7 +27,7 @@ bool fast_single_plan(const NetView& net, int cluster_size, const std::vector<st
                       FastPlan* plan, std::vector<double>* blobs);
 cudaError_t prepare_single_fast();
 cudaError_t launch_single_fast(const NetView& net, const FastPlan& plan, const double* blobs, const void* posq, const void* posq_corr,
-                               unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream);
+                               unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream, bool allow_pdl);
 // annf_batched.cu
 size_t batched_smem_bytes(const NetView& net, int extra_nodes, int tr, bool fp64);
 cudaError_t launch_batched(const NetView& net, const int* x_off, int extra_nodes, int tr, bool fp64, int R,
@@ -122,6 +122,7 @@ struct annf_context {
     int prec_single = ANNF_PREC_FP64, prec_batched = ANNF_PREC_FP64;
     int batched_path = 0;
     int cluster_size = 1;
+    bool order_dirty = true;         // sel_slots was (re)written since the last single-replica launch: that launch must not use PDL
     bool fast_single = false;        // low-latency single-replica kernel applies (Cartesian input, Tanh / Linear hidden layers)
     FastPlan fast_plan{};
     double* fast_blobs = nullptr;    // per-CTA parameter blobs of the low-latency single-replica kernel
@@ -542,6 +543,7 @@ annf_status annf_set_atom_order(annf_handle h, const int32_t* atom_index_dev, in
     invert_order_kernel<<<(num_atoms + 255) / 256, 256, 0, s>>>(atom_index_dev, num_atoms, h->inverse);
     remap_kernel<<<(h->net.n_sel + 255) / 256, 256, 0, s>>>(h->sel_atoms, h->net.n_sel, h->inverse, h->sel_slots);
     ANNF_CUDA(cudaGetLastError());
+    h->order_dirty = true;
     h->launches += 2;
     return ANNF_OK;
 }
@@ -558,7 +560,9 @@ annf_status annf_eval_openmm(annf_handle h, const void* posq, const void* posq_c
     cudaError_t err;
     if (h->fast_single) {
         h->prof.begin("annf_single_fast_kernel", s);
-        err = launch_single_fast(h->net, h->fast_plan, h->fast_blobs, posq, posq_correction, force_buffer, padded_num_atoms, energy_buffer, flags, s);
+        err = launch_single_fast(h->net, h->fast_plan, h->fast_blobs, posq, posq_correction, force_buffer, padded_num_atoms, energy_buffer, flags, s,
+                                 !h->order_dirty);
+        h->order_dirty = false;
     } else {
         h->prof.begin("annf_single_kernel", s);
         err = launch_single(h->net, h->cluster_size, posq, posq_correction, force_buffer, padded_num_atoms, energy_buffer, flags, s);

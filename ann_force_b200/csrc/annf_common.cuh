@@ -113,7 +113,7 @@ __device__ inline double output_head(int type, int n, const double* z, int zs, c
             const double p = z[(2 * j) * zs], q = z[(2 * j + 1) * zs];
             // one reciprocal instead of five divisions (each ~300 cycles of dependent fp64 latency in the single-replica
             // kernel): x / r as x * (1/r) is within 1 ulp of the reference's quotient
-            const double inv_r = 1.0 / sqrt(p * p + q * q);
+            const double inv_r = rsqrt(p * p + q * q);                // one MUFU + Newton steps instead of sqrt + divide: <= 1 ulp apart
             const double c = p * inv_r, s = q * inv_r;               // :213-216
             const int sign = s > 0 ? 1 : -1;                         // :279, .h:102
             const double angle = acos(c) * sign;
@@ -122,7 +122,7 @@ __device__ inline double output_head(int type, int n, const double* z, int zs, c
             if (fabs(d2) < fabs(dist)) dist = d2;
             if (fabs(d3) < fabs(dist)) dist = d3;
             e += 0.5 * k * fmin(fmin(d1 * d1, d2 * d2), d3 * d3);     // .h:109-114
-            const double d_cos = k * dist * (-1) / sqrt(1 - c * c) * sign;   // :292-293 ; d_sin = 0 (:294)
+            const double d_cos = k * dist * (-1) * rsqrt(1 - c * c) * sign;  // :292-293 ; d_sin = 0 (:294)
             // Circular Jacobian (:309-317) applied to (d_cos, 0): q / r^3 * (q d_cos), p / r^3 * (-q d_cos)
             const double t = q * d_cos * (inv_r * inv_r * inv_r);
             dz[(2 * j) * ds] = q * t;

@@ -615,6 +615,10 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
         if (lane == 31) cp_async8(kval, args.k_dev);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // The slot of this thread's first atom is fetched BEFORE the wait: sel_slots is written only by annf_set_atom_order, and the
+    // launcher drops the PDL attribute for the first evaluation after a reorder, so under PDL the kernel ahead of this one never
+    // is its writer.  It takes one of the two dependent global round trips (slot -> position) off the critical path.
+    const int my_slot = tid < A ? __ldg(args.sel_slots + tid) : 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");    // everything below may read what earlier kernels wrote
     ANNF_PHASE(11);
 
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
     if (!cartesian) {
         // pair distances (:152-160) or dihedral cos / sin (:125-127, :579-636) over the staged positions of the feature atoms
         for (int i = tid; i < A; i += kSingleThreads) {
-            const int slot = args.sel_slots[i];
+            const int slot = i == tid ? my_slot : args.sel_slots[i];
             slots_s[i] = slot;
             const double3 p = load_pos(args.posq, args.posq_corr, args.flags, slot);
             fpos[3 * i] = p.x; fpos[3 * i + 1] = p.y; fpos[3 * i + 2] = p.z;
@@ -648,7 +652,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
         if (warp == 0) {
             double x = 0.0, y = 0.0, w = 0.0;
             if (lane < A) {
-                const int slot = args.sel_slots[lane];
+                const int slot = my_slot;                 // warp 0: tid == lane
                 slots_s[lane] = slot;
                 const double3 p = load_pos(args.posq, args.posq_corr, args.flags, slot);
                 x = p.x * args.inv_scale; y = p.y * args.inv_scale; w = p.z * args.inv_scale;      // :139
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(kSingleThreads, 1) annf_single_fast_kernel(con
     } else {
         double sx = 0.0, sy = 0.0, sz = 0.0;
         for (int i = tid; i < A; i += kSingleThreads) {
-            const int slot = args.sel_slots[i];
+            const int slot = i == tid ? my_slot : args.sel_slots[i];
             slots_s[i] = slot;
             const double3 p = load_pos(args.posq, args.posq_corr, args.flags, slot);
             const double x = p.x * args.inv_scale, y = p.y * args.inv_scale, w = p.z * args.inv_scale;
@@ -918,7 +922,7 @@ cudaError_t prepare_single_fast() {
 }
 
 cudaError_t launch_single_fast(const NetView& net, const FastPlan& plan, const double* blobs, const void* posq, const void* posq_corr,
-                               unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream) {
+                               unsigned long long* force, int padded, void* energy, unsigned flags, cudaStream_t stream, bool allow_pdl) {
     FastArgs args;
     args.blob = blobs;
     args.blob_doubles = plan.blob_doubles;
@@ -954,8 +958,10 @@ cudaError_t launch_single_fast(const NetView& net, const FastPlan& plan, const d
     attr[1].val.clusterDim.x = plan.cl;
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = plan.cl == 1 ? 1 : 2;
+    // allow_pdl == false (the first evaluation after annf_set_atom_order): a plain, fully serialised launch — the kernel reads
+    // sel_slots before griddepcontrol.wait
+    cfg.attrs = allow_pdl ? attr : attr + 1;
+    cfg.numAttrs = (allow_pdl ? 1 : 0) + (plan.cl == 1 ? 0 : 1);
     if (plan.cl == 1) return cudaLaunchKernelEx(&cfg, annf_single_fast_kernel<false>, args);
     return cudaLaunchKernelEx(&cfg, annf_single_fast_kernel<true>, args);
 }
