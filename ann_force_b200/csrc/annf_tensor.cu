@@ -92,6 +92,7 @@ struct GemmParams {
     float* gs_scratch;                // [tiles][gsplit][BM][BN] fp32 partial tiles
     int* gs_arrive;                   // [tiles] partial tiles published so far (self-resetting)
     int* gs_done;                     // [tiles] CTAs that have finished reading (the last one resets both counters)
+    int no_b_prefetch;                // experiments (ANNF_TENSOR_B_PREFETCH=0): request the weights only after the dependency wait
     int direct_store;                 // EPI_FORCE, unsplit, identity selection, 16-byte aligned rows: the tile leaves through tm_out (TMA store)
     int dbg;                          // diagnostic builds: slot of g_tensor_clock this launch records into (-1: none)
     int chunk;                        // K-blocks accumulated in TMEM between two promotions into the fp32 register accumulators
@@ -437,11 +438,14 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const 
         }
         return q;
     };
-    Group next = fetch(0);
+    // two groups ahead: a group's loads are S DSMEM round trips issued together (~1 us each under load), and a CTA finishes only
+    // 4 - 8 groups per thread, so the depth of the prefetch is most of the loop's duration
+    Group n1 = fetch(0), n2 = fetch(1);
 #pragma unroll 1
     for (int g = 0; g < kGroups; g++) {
-        const Group cur = next;
-        next = fetch(g + 1);
+        const Group cur = n1;
+        n1 = n2;
+        n2 = fetch(g + 2);
         if (cur.ok) epilogue_finish<KIND>(p, cur.m, cur.n, cur.sum, cur.aux);
     }
 }
@@ -589,6 +593,57 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 1);
+    // One pipeline stage of K-block i: arm the stage's barrier, load the A rows (activations: written by the kernel before this
+    // one) and / or the B rows (weights: static).  Called by the producer thread only.
+    auto issue_stage = [&](int i, bool do_a, bool do_b, bool arm) {
+        const int s = i % kStages;
+        const uint32_t full = smem_u32(&bar_full[s]);
+        const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
+        const int kc = (kb0 + i) * BK;
+        if (CG == 2) {
+            const uint32_t full_leader = map_to_cta(full, leader_cta);
+            if (arm) {
+                if (pair_rank == 0) mbar_expect_tx(full, (uint32_t) (2 * Cfg::kStageBytes));   // both CTAs' bytes land here
+                else mbar_arrive_cluster(full_leader);
+            }
+            if (do_a) {
+                tma_load_2d_pair(base, &tm_a_hi, full_leader, kc, m0);
+                tma_load_2d_pair(base + BM * kBlockBytes, &tm_a_lo, full_leader, kc, m0);
+            }
+            if (do_b) {
+#pragma unroll
+                for (int h = 0; h < kBRows / kBBox; h++) {
+                    tma_load_2d_pair(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
+                    tma_load_2d_pair(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
+                }
+            }
+        } else {
+            if (arm) mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
+            if (do_a) {
+                if (NX == 2) {
+                    // own half of the A rows to both CTAs (the maps have 64-row boxes); the other half arrives from the peer
+                    const uint32_t half = (uint32_t) x_rank * (BM / 2) * kBlockBytes;
+                    tma_load_2d_mc(base + half, &tm_a_hi, full, kc, m0 + x_rank * (BM / 2), mc_mask);
+                    tma_load_2d_mc(base + BM * kBlockBytes + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask);
+                } else {
+                    tma_load_2d(base, &tm_a_hi, full, kc, m0);
+                    tma_load_2d(base + BM * kBlockBytes, &tm_a_lo, full, kc, m0);
+                }
+            }
+            if (do_b) {
+#pragma unroll
+                for (int h = 0; h < kBRows / kBBox; h++) {                        // TMA boxes are at most 256 rows; use 128-row boxes
+                    tma_load_2d(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox);
+                    tma_load_2d(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox);
+                }
+            }
+        }
+    };
+    // The weights do not depend on the kernel before this one: the first stages are armed and their B halves requested BEFORE the
+    // dependency wait, so that after it only the A halves are still on their way (the wait-to-first-MMA gap was 1.6 - 1.9 us).
+    const int npre = (p.dry || p.no_b_prefetch) ? 0 : min(kStages, num_kb);
+    if (warp == kEpiWarps && lane == 0)
+        for (int i = 0; i < npre; i++) issue_stage(i, false, true, true);
     pdl_wait();                                             // everything below reads what earlier kernels wrote
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 2);
     if (warp == kEpiWarps + 2) {
@@ -660,53 +715,25 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             // ----- TMA producer (every CTA stages its own operand rows) -----
             if (lane == 0) {
                 for (int i = 0; i < num_kb; i++) {
+                    if (i < npre) {                                               // armed, and its B half issued, before the dependency wait
+                        if (i == 0) ANNF_TMARK(p.dbg, 3);
+                        issue_stage(i, true, false, false);
+                        continue;
+                    }
                     const int s = i % kStages;
                     const uint32_t ph = (uint32_t) (i / kStages) & 1u;
                     { ANNF_TWAIT_BEGIN();
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free (in both CTAs of a pair)
                     ANNF_TWAIT_END(p.dbg, 21); }
-                    const uint32_t full = smem_u32(&bar_full[s]);
                     if (p.dry & 4) {                                              // experiments: no TMA traffic
+                        const uint32_t full = smem_u32(&bar_full[s]);
                         if (CG == 2 && pair_rank == 1) mbar_arrive_cluster(map_to_cta(full, leader_cta));
                         else if (CG == 2) mbar_expect_tx(full, 0);
                         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
                         continue;
                     }
-                    const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
-                    const int kc = (kb0 + i) * BK;
                     if (i == 0) ANNF_TMARK(p.dbg, 3);
-                    if (CG == 2) {
-                        const uint32_t full_leader = map_to_cta(full, leader_cta);
-                        if (pair_rank == 0) mbar_expect_tx(full, (uint32_t) (2 * Cfg::kStageBytes));   // both CTAs' bytes land here
-                        else mbar_arrive_cluster(full_leader);
-                        tma_load_2d_pair(base, &tm_a_hi, full_leader, kc, m0);
-                        tma_load_2d_pair(base + BM * kBlockBytes, &tm_a_lo, full_leader, kc, m0);
-#pragma unroll
-                        for (int h = 0; h < kBRows / kBBox; h++) {
-                            tma_load_2d_pair(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
-                            tma_load_2d_pair(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
-                        }
-                    } else if (NX == 2) {
-                        // own half of the A rows to both CTAs (the maps have 64-row boxes); the other half arrives from the peer
-                        mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
-                        const uint32_t half = (uint32_t) x_rank * (BM / 2) * kBlockBytes;
-                        tma_load_2d_mc(base + half, &tm_a_hi, full, kc, m0 + x_rank * (BM / 2), mc_mask);
-                        tma_load_2d_mc(base + BM * kBlockBytes + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask);
-#pragma unroll
-                        for (int h = 0; h < kBRows / kBBox; h++) {
-                            tma_load_2d(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox);
-                            tma_load_2d(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox);
-                        }
-                    } else {
-                        mbar_expect_tx(full, (uint32_t) Cfg::kStageBytes);
-                        tma_load_2d(base, &tm_a_hi, full, kc, m0);
-                        tma_load_2d(base + BM * kBlockBytes, &tm_a_lo, full, kc, m0);
-#pragma unroll
-                        for (int h = 0; h < kBRows / kBBox; h++) {                // TMA boxes are at most 256 rows; use 128-row boxes
-                            tma_load_2d(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox);
-                            tma_load_2d(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox);
-                        }
-                    }
+                    issue_stage(i, true, true, true);
                 }
             }
         } else if (warp == kEpiWarps + 1 && pair_rank == 0) {
@@ -1636,6 +1663,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         gp.out_hi = p.d1_hi; gp.out_lo = p.d1_lo; gp.ld_out = p.ld1;
         gp.a_exp = nullptr; gp.b_exp = nullptr; gp.out_exp = nullptr; gp.aux_exp = nullptr;   // staged in `vec`
         gp.sel_atoms = nullptr; gp.direct_store = 0; gp.dbg = -1; gp.chunk = 1; gp.dry = 0;
+        gp.no_b_prefetch = 0;
         gp.gsplit = 0; gp.gs_scratch = nullptr; gp.gs_arrive = nullptr; gp.gs_done = nullptr;
         for (int t = rank; t < tiles1; t += CL) {
             drain(nkb2);
@@ -1739,6 +1767,7 @@ struct TensorPlan {
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
+    bool no_b_prefetch = false;                     // ANNF_TENSOR_B_PREFETCH=0
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
 
@@ -1842,6 +1871,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
     if (const char* env = getenv("ANNF_GEMM_SPLIT_SHORTK")) t->force_split = atoi(env);
     if (const char* env = getenv("ANNF_TENSOR_DRY")) t->dry = atoi(env);
+    if (const char* env = getenv("ANNF_TENSOR_B_PREFETCH")) t->no_b_prefetch = atoi(env) == 0;
     if (const char* env = getenv("ANNF_TENSOR_DIRECT_STORE")) t->no_direct_store = atoi(env) == 0;
     // fp16 pairs: one K-block (64 values, 12 chained MMAs) per TMEM chunk; TF32 pairs: two (64 values, 24 chained MMAs).
     // Measured at BASELINE C5 (64 replicas against the reference, profiles/r02_chunk_sweep.md): the energy error grows with
@@ -2072,6 +2102,7 @@ static cudaError_t launch_gemm(TensorPlan* t, PlanSlot* sl, const GemmOp& op_in,
     GemmParams p = op.p;
     p.M = R;
     p.dry = t->dry;
+    p.no_b_prefetch = t->no_b_prefetch ? 1 : 0;
     p.chunk = t->chunk;
     p.dbg = t->dbg_next < 8 ? t->dbg_next++ : -1;
     if (p.epi == EPI_FORCE) {
