@@ -438,14 +438,13 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const 
         }
         return q;
     };
-    // two groups ahead: a group's loads are S DSMEM round trips issued together (~1 us each under load), and a CTA finishes only
-    // 4 - 8 groups per thread, so the depth of the prefetch is most of the loop's duration
-    Group n1 = fetch(0), n2 = fetch(1);
+    // one group ahead.  (Two ahead measured slower at BASELINE C5: epilogues 2.6 / 2.3 / 3.0 -> 2.7 / 2.7 / 4.3 us on the three
+    // split-K GEMMs — more DSMEM requests in flight per thread did not shorten the round trips.)
+    Group next = fetch(0);
 #pragma unroll 1
     for (int g = 0; g < kGroups; g++) {
-        const Group cur = n1;
-        n1 = n2;
-        n2 = fetch(g + 2);
+        const Group cur = next;
+        next = fetch(g + 1);
         if (cur.ok) epilogue_finish<KIND>(p, cur.m, cur.n, cur.sum, cur.aux);
     }
 }
