@@ -92,7 +92,6 @@ struct GemmParams {
     float* gs_scratch;                // [tiles][gsplit][BM][BN] fp32 partial tiles
     int* gs_arrive;                   // [tiles] partial tiles published so far (self-resetting)
     int* gs_done;                     // [tiles] CTAs that have finished reading (the last one resets both counters)
-    int push_reduce;                  // split-K partial rows are PUSHED to the CTA that finishes them (short-K GEMMs, 128-wide tiles)
     int no_b_prefetch;                // experiments (ANNF_TENSOR_B_PREFETCH=0): request the weights only after the dependency wait
     int direct_store;                 // EPI_FORCE, unsplit, identity selection, 16-byte aligned rows: the tile leaves through tm_out (TMA store)
     int dbg;                          // diagnostic builds: slot of g_tensor_clock this launch records into (-1: none)
@@ -407,18 +406,13 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
 // this code runs a handful of times per CTA, so its size is paid in instruction-cache misses — ~170 cycles per 128-byte
 // line of cold code — and an unrolled body with 16 inlined tanhf was most of the 4-6 us this epilogue used to take.
 template <int KIND, int BN, int S, int CG, int kGroupThreads, int CX = CG>
-__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const EpiVec& vec, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t,
-                                                     bool push = false) {
+__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const EpiVec& vec, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int kRows = (BM + S - 1) / S;                                        // rows this CTA finishes (S = 3: 43, 43, 42)
     constexpr int kVecPerRow = BN / 4;
     float* staging = reinterpret_cast<float*>(data);
     const float* peer[S];
-    if (push) {
-        // push mode: `data` is this CTA's receive buffer, [S][kRows][BN] with swizzled 16-byte units — all local
-#pragma unroll
-        for (int r = 0; r < S; r++) peer[r] = staging + (size_t) r * kRows * BN;
-    } else if (S > 1) {
+    if (S > 1) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
         for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, pair_rank + CX * r);   // same x position, split r
@@ -438,9 +432,7 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const 
             q.aux = epilogue_load<KIND>(p, vec, q.m, q.n, row, col);
 #pragma unroll
             for (int r = 0; r < S; r++) {                                          // fixed order: deterministic
-                const int lrow = row - rank * kRows, j4 = col >> 2;
-                const float4 x = push ? *reinterpret_cast<const float4*>(peer[r] + (size_t) lrow * BN + 4 * ((j4 & ~7) | ((j4 & 7) ^ (lrow & 7))))
-                                      : *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
+                const float4 x = *reinterpret_cast<const float4*>(peer[r] + (size_t) row * Cfg::kStagingLd + col);
                 q.sum.x += x.x; q.sum.y += x.y; q.sum.z += x.z; q.sum.w += x.w;
             }
         }
@@ -560,14 +552,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const int kChunk = p.chunk;
     const int num_chunks = (num_kb + kChunk - 1) / kChunk;
     const bool direct = p.direct_store != 0;                // unsplit force GEMM: registers -> swizzled tile -> TMA store
-    // Push-mode split-K reduction (short-K GEMMs on 128 x 128 tiles): the pipeline runs on two of the three stage buffers and the
-    // third RECEIVES the partial rows the peer CTAs of the cluster push into it (st to DSMEM) as soon as they have drained their
-    // accumulators — nobody waits for this CTA's main loop, because its pipeline never touches that buffer.  After the cluster
-    // barrier every CTA sums its rows from its OWN shared memory; pulling them from the peers cost a DSMEM round trip per group
-    // (epilogues 2.3 - 3.0 us on the 1024 x 512 x 512 GEMMs of BASELINE C5).
-    constexpr bool kPushOk = S > 1 && CG == 1 && NX == 1 && BN == 128 && BM % S == 0 && Cfg::kStages == 3;
-    const bool push = kPushOk && p.push_reduce != 0;
-    const int nst = push ? 2 : kStages;                     // stage buffers the pipeline cycles through
 
     ANNF_TGRID_START(p.dbg);
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 0);
@@ -611,7 +595,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     // One pipeline stage of K-block i: arm the stage's barrier, load the A rows (activations: written by the kernel before this
     // one) and / or the B rows (weights: static).  Called by the producer thread only.
     auto issue_stage = [&](int i, bool do_a, bool do_b, bool arm) {
-        const int s = i % nst;
+        const int s = i % kStages;
         const uint32_t full = smem_u32(&bar_full[s]);
         const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
         const int kc = (kb0 + i) * BK;
@@ -656,7 +640,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     };
     // The weights do not depend on the kernel before this one: the first stages are armed and their B halves requested BEFORE the
     // dependency wait, so that after it only the A halves are still on their way (the wait-to-first-MMA gap was 1.6 - 1.9 us).
-    const int npre = (p.dry || p.no_b_prefetch) ? 0 : min(nst, num_kb);
+    const int npre = (p.dry || p.no_b_prefetch) ? 0 : min(kStages, num_kb);
     if (warp == kEpiWarps && lane == 0)
         for (int i = 0; i < npre; i++) issue_stage(i, false, true, true);
     pdl_wait();                                             // everything below reads what earlier kernels wrote
@@ -718,8 +702,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 }
             }
         } else if (participates && !(p.dry & 8) && !(S == 1 && direct))
-            cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, push ? data + (size_t) 2 * Cfg::kStageBytes : data, rank, x_rank, m0, n0,
-                                                                   (int) threadIdx.x, push);
+            cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, data, rank, x_rank, m0, n0, (int) threadIdx.x);
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
         role_sync<(S > 1 || CX == 2)>();                    // nobody leaves while peers still read / share TMEM
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
@@ -736,8 +719,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         issue_stage(i, true, false, false);
                         continue;
                     }
-                    const int s = i % nst;
-                    const uint32_t ph = (uint32_t) (i / nst) & 1u;
+                    const int s = i % kStages;
+                    const uint32_t ph = (uint32_t) (i / kStages) & 1u;
                     { ANNF_TWAIT_BEGIN();
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                  // slot free (in both CTAs of a pair)
                     ANNF_TWAIT_END(p.dbg, 21); }
@@ -769,8 +752,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     const int i_end = min(num_kb, (c + 1) * kChunk);
                     bool first = true;
                     for (; i < i_end; i++) {
-                        const int s = i % nst;
-                        const uint32_t ph = (uint32_t) (i / nst) & 1u;
+                        const int s = i % kStages;
+                        const uint32_t ph = (uint32_t) (i / kStages) & 1u;
                         { ANNF_TWAIT_BEGIN();
                         mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed (both CTAs)
                         ANNF_TWAIT_END(p.dbg, 20); }
@@ -866,17 +849,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     if (n0 + cb * 32 < p.N) tma_store_2d(&tm_out, smem_u32(data + (size_t) cb * (BM * 128)), n0 + cb * 32, m0);
                 tma_store_commit_and_wait_read();                                  // shared memory has been read: the CTA may leave
             }
-        } else if (push) {
-            // push this thread's row of the partial tile to the CTA that finishes it (possibly this one): 32 x 16 bytes, the 16-byte
-            // unit index XORed with the row so that neither the writes of a warp nor the row-wise reads collide on banks
-            constexpr int kRows = BM / (S > 1 ? S : 1);
-            const int owner = row / kRows, lrow = row - owner * kRows;
-            float* recv_local = reinterpret_cast<float*>(data + (size_t) 2 * Cfg::kStageBytes);
-            float* dst = cg::this_cluster().map_shared_rank(recv_local, (unsigned) owner) + ((size_t) rank * kRows + lrow) * BN;
-#pragma unroll
-            for (int j4 = 0; j4 < kColsPerWarp / 4; j4++)
-                *reinterpret_cast<float4*>(dst + 4 * ((j4 & ~7) | ((j4 & 7) ^ (lrow & 7)))) =
-                    make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
         } else {
             // park the tile in shared memory (all TMA loads have landed and been consumed: the stage buffers are free).
             // Unsplit GEMMs do this too: the epilogue below then walks ROWS with consecutive lanes, i.e. 512-byte coalesced
@@ -1690,7 +1662,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         gp.out_hi = p.d1_hi; gp.out_lo = p.d1_lo; gp.ld_out = p.ld1;
         gp.a_exp = nullptr; gp.b_exp = nullptr; gp.out_exp = nullptr; gp.aux_exp = nullptr;   // staged in `vec`
         gp.sel_atoms = nullptr; gp.direct_store = 0; gp.dbg = -1; gp.chunk = 1; gp.dry = 0;
-        gp.no_b_prefetch = 0; gp.push_reduce = 0;
+        gp.no_b_prefetch = 0;
         gp.gsplit = 0; gp.gs_scratch = nullptr; gp.gs_arrive = nullptr; gp.gs_done = nullptr;
         for (int t = rank; t < tiles1; t += CL) {
             drain(nkb2);
@@ -1794,7 +1766,6 @@ struct TensorPlan {
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
-    bool no_push_reduce = false;                    // ANNF_TENSOR_PUSH_REDUCE=0: always pull the split-K partials through DSMEM
     bool no_b_prefetch = false;                     // ANNF_TENSOR_B_PREFETCH=0
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
@@ -1899,7 +1870,6 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
     if (const char* env = getenv("ANNF_GEMM_SPLIT_SHORTK")) t->force_split = atoi(env);
     if (const char* env = getenv("ANNF_TENSOR_DRY")) t->dry = atoi(env);
-    if (const char* env = getenv("ANNF_TENSOR_PUSH_REDUCE")) t->no_push_reduce = atoi(env) == 0;
     if (const char* env = getenv("ANNF_TENSOR_B_PREFETCH")) t->no_b_prefetch = atoi(env) == 0;
     if (const char* env = getenv("ANNF_TENSOR_DIRECT_STORE")) t->no_direct_store = atoi(env) == 0;
     // fp16 pairs: one K-block (64 values, 12 chained MMAs) per TMEM chunk; TF32 pairs: two (64 values, 24 chained MMAs).
@@ -2235,8 +2205,6 @@ static cudaError_t launch_gemm(TensorPlan* t, PlanSlot* sl, const GemmOp& op_in,
     const int tiles = ((p.N + bn - 1) / bn) * ((R + BM - 1) / BM);
     int s = pick_split(tiles, kb, t->sm_count);
     if (t->force_split > 0 && kb <= 32 && p.epi != EPI_FORCE) s = t->force_split;      // experiments: ANNF_GEMM_SPLIT_SHORTK
-    // push-mode reduction: the pipeline gives up its third stage buffer, so only where a CTA walks few K-blocks anyway
-    p.push_reduce = (bn == 128 && s > 1 && (kb + s - 1) / s <= 4 && !t->no_push_reduce) ? 1 : 0;
     if (bn == 256) {
         switch (s) {
         case 8: return launch_gemm_t<KIND, 256, 8, 1>(op, p, stream);
