@@ -495,10 +495,18 @@ __device__ __forceinline__ void global_split_epilogue(const GemmParams& p, const
 }
 
 // Block- or cluster-wide rendezvous used by every warp role at the same two points of the kernel.
-template <bool kCluster> __device__ __forceinline__ void role_sync() {
+// kOrderMemory = false: execution ordering only ("nobody leaves while peers may still read its shared memory").  The release
+// form of the cluster barrier compiles to MEMBAR.ALL.GPU, which at the end of a kernel waits for every global store of the
+// epilogue to be acknowledged by L2 — visibility the NEXT kernel gets from the grid dependency anyway.
+template <bool kCluster, bool kOrderMemory = true> __device__ __forceinline__ void role_sync() {
     if (kCluster) {
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (kOrderMemory) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else {
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+        }
     } else {
         asm volatile("bar.sync 0;" ::: "memory");
     }
@@ -719,7 +727,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, data, rank, x_rank, m0, n0, (int) threadIdx.x, dry);
         if (dry) return;
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
-        role_sync<(S > 1 || CX == 2)>();                    // nobody leaves while peers still read / share TMEM
+        role_sync<(S > 1 || CX == 2), false>();             // nobody leaves while peers still read / share TMEM (execution order only)
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
     };
     if (warp >= kEpiWarps) {
