@@ -204,6 +204,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_cpus(local_rank) if world > 1 else None     # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -536,11 +537,31 @@ def main():
                             graph_steps=graph_steps if graph is not None else 0, buffer_sets=nbuf),
                 clocks=sampler.summary(), e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                 ns_per_day_per_replica=steps_per_s_per_replica * TIMESTEP_FS * 1e-6 * 86400.0,
-                exchange_allgather_us=exchange_us, parity=parity, other_workloads=others)
+                exchange_allgather_us=exchange_us, cpu_affinity=affinity, parity=parity, other_workloads=others)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bind_to_gpu_cpus(device_index):
+    """Multi-rank runs: restrict this process to the CPUs NVML reports as closest to its GPU (same NUMA node / root complex),
+    intersected with what the container allows, so that its pinned host buffers and its submission thread sit next to the
+    link they feed.  Returns a short description for the JSON line; never fatal."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        chosen = sorted(ideal & allowed)
+        if chosen:
+            os.sched_setaffinity(0, chosen)
+            return "gpu %d -> cpus %d-%d (%d of %d allowed)" % (device_index, chosen[0], chosen[-1], len(chosen), len(allowed))
+        return "gpu %d: none of its %d ideal cpus is in the allowed set of %d" % (device_index, len(ideal), len(allowed))
+    except Exception as exc:       # noqa: BLE001
+        return "unavailable: %s" % str(exc)[:80]
 
 
 def parity_check(kernel, force, single, ctx, coords0, centers, centers_np, n_sample=64):
