@@ -1195,7 +1195,6 @@ __device__ __forceinline__ float load_pair(const void* hi, const void* lo, int m
 // that runs once per CTA; rolled, its 128 fat CTAs delayed the cluster GEMM that follows under PDL: step 110 -> 121 us.)
 constexpr int kHeadThreads = 128;
 constexpr int kHeadMaxOut = 64;
-constexpr int kHeadBatch = 2;
 template <int KIND>
 __global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int R, const float* __restrict__ centers,
                                                            const void* __restrict__ a_hi, const void* __restrict__ a_lo, int ld,
@@ -1220,26 +1219,39 @@ __global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int 
     const elem* ah = static_cast<const elem*>(a_hi) + (size_t) r * ld;
     const elem* al = static_cast<const elem*>(a_lo) + (size_t) r * ld;
     const float a_unscale = KIND == KIND_F16 ? exp2i(-chain.x_exp[L - 2][r]) : 1.f;
-    // The loop is bound by global-load latency unless many loads are in flight: kHeadBatch hidden units per thread per pass, their
-    // activations and kHeadBatch x 8 weights all loaded before the dependent fp64 FMAs.  Two, not four: 7 CTAs per SM (72 registers)
-    // keep all 1024 CTAs of a BASELINE C5 batch resident at once; at 96 registers they ran in two waves.
+    // Every thread owns FOUR CONSECUTIVE hidden units per pass (nH is a multiple of 4 on this path): the activation pair arrives
+    // as two 8-byte loads, an output's weights as two 16-byte loads — a quarter of the load instructions of a strided mapping,
+    // and whole 256-byte lines per warp.  (The kernel is instruction-issue bound: 5.0 M warp-instructions for 8.4 MFLOP before.)
+    auto load_act4 = [&](int m4, float (&av)[4]) {
+        if (KIND == KIND_F16) {
+            const float4 h = half4_to_float4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(ah) + m4)));
+            const float4 l = half4_to_float4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(al) + m4)));
+            av[0] = (h.x + l.x) * a_unscale; av[1] = (h.y + l.y) * a_unscale; av[2] = (h.z + l.z) * a_unscale; av[3] = (h.w + l.w) * a_unscale;
+        } else {
+            const float4 h = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ah) + m4));
+            const float4 l = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(al) + m4));
+            av[0] = h.x + l.x; av[1] = h.y + l.y; av[2] = h.z + l.z; av[3] = h.w + l.w;      // hi + lo is exact in fp32
+        }
+    };
     for (int j0 = 0; j0 < nL; j0 += 8) {                    // 8 outputs at a time: 8 independent accumulators per thread
         double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int mb = tid; mb < nH; mb += kHeadBatch * kHeadThreads) {
-            float av[kHeadBatch];
-            double w[kHeadBatch][8];
+        for (int m4 = 4 * tid; m4 < nH; m4 += 4 * kHeadThreads) {
+            float av[4];
+            load_act4(m4, av);
+            double2 w[8][2];
 #pragma unroll
-            for (int v = 0; v < kHeadBatch; v++) {
-                const int m = mb + v * kHeadThreads;
-                av[v] = m < nH ? load_pair<KIND>(ah, al, m, a_unscale) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; u++) w[v][u] = (m < nH && j0 + u < nL) ? __ldg(W + (size_t) (j0 + u) * nH + m) : 0.0;
+            for (int u = 0; u < 8; u++) {
+                const bool in = j0 + u < nL;
+                const double2* wp = reinterpret_cast<const double2*>(W + (size_t) (j0 + u) * nH + m4);
+                w[u][0] = in ? __ldg(wp) : make_double2(0.0, 0.0);
+                w[u][1] = in ? __ldg(wp + 1) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int v = 0; v < kHeadBatch; v++) {
-                const double a = (double) av[v];
-#pragma unroll
-                for (int u = 0; u < 8; u++) acc[u] = fma(w[v][u], a, acc[u]);
+            for (int u = 0; u < 8; u++) {
+                acc[u] = fma(w[u][0].x, (double) av[0], acc[u]);
+                acc[u] = fma(w[u][0].y, (double) av[1], acc[u]);
+                acc[u] = fma(w[u][1].x, (double) av[2], acc[u]);
+                acc[u] = fma(w[u][1].y, (double) av[3], acc[u]);
             }
         }
 #pragma unroll
@@ -1280,41 +1292,30 @@ __global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int 
             }
         }
     }
-    // the result is re-split to operand pairs: fp32 FMA is enough here.  Same batching: 4 hidden units per pass, loads first.
-    for (int mb = tid; mb < nH; mb += 4 * kHeadThreads) {
+    // the result is re-split to operand pairs: fp32 FMA is enough here.  Four consecutive hidden units per thread, vector loads.
+    for (int m4 = 4 * tid; m4 < nH; m4 += 4 * kHeadThreads) {
         float av[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const int m = mb + v * kHeadThreads;
-            av[v] = m < nH ? load_pair<KIND>(ah, al, m, a_unscale) : 0.f;
-        }
+        load_act4(m4, av);
         for (int j = 0; j < nL; j++) {
-            float w[4];
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const int m = mb + v * kHeadThreads;
-                w[v] = m < nH ? __ldg(W32 + (size_t) j * nH + m) : 0.f;
-            }
-#pragma unroll
-            for (int v = 0; v < 4; v++) acc[v] = fmaf(w[v], dzf[j], acc[v]);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W32 + (size_t) j * nH + m4));
+            const float dj = dzf[j];
+            acc[0] = fmaf(w.x, dj, acc[0]); acc[1] = fmaf(w.y, dj, acc[1]); acc[2] = fmaf(w.z, dj, acc[2]); acc[3] = fmaf(w.w, dj, acc[3]);
         }
+        if (hidden_type == ANNF_TANH) {
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const int m = mb + v * kHeadThreads;
-            if (m >= nH) continue;
-            float r = acc[v];
-            if (hidden_type == ANNF_TANH) r *= (1.f - av[v] * av[v]);
-            if (KIND == KIND_F16) {
-                const float rs = r * d_scale;
-                const __half hi = __float2half_rn(rs);
-                static_cast<__half*>(d_hi)[(size_t) r_index * ld + m] = hi;
-                static_cast<__half*>(d_lo)[(size_t) r_index * ld + m] = __float2half_rn(rs - __half2float(hi));
-            } else {
-                float hi, lo;
-                split_tf32(r, hi, lo);
-                static_cast<float*>(d_hi)[(size_t) r_index * ld + m] = hi;
-                static_cast<float*>(d_lo)[(size_t) r_index * ld + m] = lo;
-            }
+            for (int v = 0; v < 4; v++) acc[v] *= (1.f - av[v] * av[v]);
+        }
+        if (KIND == KIND_F16) {
+            uint2 hi, lo;
+            split_f16x4(make_float4(acc[0] * d_scale, acc[1] * d_scale, acc[2] * d_scale, acc[3] * d_scale), hi, lo);
+            *reinterpret_cast<uint2*>(static_cast<__half*>(d_hi) + (size_t) r_index * ld + m4) = hi;
+            *reinterpret_cast<uint2*>(static_cast<__half*>(d_lo) + (size_t) r_index * ld + m4) = lo;
+        } else {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) split_tf32(acc[v], hi[v], lo[v]);
+            *reinterpret_cast<float4*>(static_cast<float*>(d_hi) + (size_t) r_index * ld + m4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(static_cast<float*>(d_lo) + (size_t) r_index * ld + m4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
     if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
