@@ -92,7 +92,6 @@ struct GemmParams {
     float* gs_scratch;                // [tiles][gsplit][BM][BN] fp32 partial tiles
     int* gs_arrive;                   // [tiles] partial tiles published so far (self-resetting)
     int* gs_done;                     // [tiles] CTAs that have finished reading (the last one resets both counters)
-    int no_warm_epilogue;             // experiments (ANNF_TENSOR_WARM_EPILOGUE=0)
     int no_b_prefetch;                // experiments (ANNF_TENSOR_B_PREFETCH=0): request the weights only after the dependency wait
     int direct_store;                 // EPI_FORCE, unsplit, identity selection, 16-byte aligned rows: the tile leaves through tm_out (TMA store)
     int dbg;                          // diagnostic builds: slot of g_tensor_clock this launch records into (-1: none)
@@ -356,12 +355,11 @@ __device__ __forceinline__ EpiAux epilogue_load(const GemmParams& p, const EpiVe
     return x;
 }
 
-// dry: everything but the stores (the instruction-cache warm-up pass, see gemm3x_kernel)
 template <int KIND>
-__device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int n, float4 v, const EpiAux& x, bool dry = false) {
+__device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int n, float4 v, const EpiAux& x) {
     if (KIND == KIND_F16) { v.x *= x.unscale.x; v.y *= x.unscale.y; v.z *= x.unscale.z; v.w *= x.unscale.w; }
     if (p.epi == EPI_STORE) {
-        if (!dry) *reinterpret_cast<float4*>(static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out + n) = v;
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out + n) = v;
         return;
     }
     if (p.epi == EPI_FORCE) {
@@ -370,7 +368,6 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
         // (ANN_ReferenceKernels.cpp:137-145, :397-410), so the accumulator already IS the force.
         const float4 f = v;
         float* row = static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out;
-        if (dry) return;
         if (p.sel_atoms == nullptr) {
             *reinterpret_cast<float4*>(row + n) = f;
         } else {
@@ -393,14 +390,12 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
     if (KIND == KIND_F16) {
         uint2 hi, lo;
         split_f16x4(make_float4(v.x * x.out_scale, v.y * x.out_scale, v.z * x.out_scale, v.w * x.out_scale), hi, lo);
-        if (dry && hi.x != 0x7fc07fc1u) return;     // never true for a split pair (hi would be two different NaNs): keeps the math alive
         *reinterpret_cast<uint2*>(static_cast<__half*>(p.out_hi) + (size_t) m * p.ld_out + n) = hi;
         *reinterpret_cast<uint2*>(static_cast<__half*>(p.out_lo) + (size_t) m * p.ld_out + n) = lo;
         return;
     }
     float4 hi, lo;
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-    if (dry && __float_as_uint(hi.x) != 0x7fc00001u) return;
     *reinterpret_cast<float4*>(static_cast<float*>(p.out_hi) + (size_t) m * p.ld_out + n) = hi;
     *reinterpret_cast<float4*>(static_cast<float*>(p.out_lo) + (size_t) m * p.ld_out + n) = lo;
 }
@@ -411,22 +406,18 @@ __device__ __forceinline__ void epilogue_finish(const GemmParams& p, int m, int 
 // this code runs a handful of times per CTA, so its size is paid in instruction-cache misses — ~170 cycles per 128-byte
 // line of cold code — and an unrolled body with 16 inlined tanhf was most of the 4-6 us this epilogue used to take.
 template <int KIND, int BN, int S, int CG, int kGroupThreads, int CX = CG>
-__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const EpiVec& vec, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t,
-                                                     bool dry = false) {
+__device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const EpiVec& vec, unsigned char* data, int rank, int pair_rank, int m0, int n0, int t) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int kRows = (BM + S - 1) / S;                                        // rows this CTA finishes (S = 3: 43, 43, 42)
     constexpr int kVecPerRow = BN / 4;
     float* staging = reinterpret_cast<float*>(data);
     const float* peer[S];
-    if (S > 1 && !dry) {
+    if (S > 1) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
         for (int r = 0; r < S; r++) peer[r] = cluster.map_shared_rank(staging, pair_rank + CX * r);   // same x position, split r
     } else {
-        // dry (warm-up) pass: the peers may not even have started, so every "peer" is this CTA's own shared memory — the same
-        // instructions, other addresses
-#pragma unroll
-        for (int r = 0; r < S; r++) peer[r] = staging;
+        peer[0] = staging;
     }
     constexpr int kGroups = (kRows * kVecPerRow + kGroupThreads - 1) / kGroupThreads;   // groups per thread
     struct Group { EpiAux aux; float4 sum; int m, n; bool ok; };
@@ -454,7 +445,7 @@ __device__ __forceinline__ void cooperative_epilogue(const GemmParams& p, const 
     for (int g = 0; g < kGroups; g++) {
         const Group cur = next;
         next = fetch(g + 1);
-        if (cur.ok) epilogue_finish<KIND>(p, cur.m, cur.n, cur.sum, cur.aux, dry);
+        if (cur.ok) epilogue_finish<KIND>(p, cur.m, cur.n, cur.sum, cur.aux);
     }
 }
 
@@ -682,15 +673,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     // share of it.  BN = 256: one instance per role, INSIDE the region governed by that role's setmaxnreg (the producer
     // warpgroup gave its registers away and only keeps the rendezvous; code after the roles re-join could not assume either
     // register budget).
-    // dry = the instruction-cache warm-up pass: the spare warp walks the epilogue's code (no barriers, no stores, its own shared
-    // memory standing in for the peers') while the main loop runs.  The epilogue executes a handful of times per CTA, so its
-    // instructions were being fetched cold — ~170 cycles per 128-byte line, the kernels of a step evict each other from the
-    // 32 KB instruction cache — on the critical path after the last MMA.
-    auto finish_tile = [&](bool participates, bool dry = false) {
-        if (!dry) role_sync<(S > 1 || NX == 2)>();          // every partial tile (of the split) is parked; NX = 2: the peer no longer multicasts into this CTA's stages
-        if (threadIdx.x == 0 && !dry) ANNF_TMARK(p.dbg, 7);
+    auto finish_tile = [&](bool participates) {
+        role_sync<(S > 1 || NX == 2)>();                    // every partial tile (of the split) is parked; NX = 2: the peer no longer multicasts into this CTA's stages
+        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 7);
         if (S == 1 && gs > 1) {
-            if (dry) return;
             if (participates && !(p.dry & 8)) {
                 // publish this CTA's partial tile, meet the other K ranges of the tile, finish 1 / gs of its rows
                 const int n_tiles = (int) gridDim.x / CG;
@@ -724,8 +710,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 }
             }
         } else if (participates && !(p.dry & 8) && !(S == 1 && direct))
-            cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, data, rank, x_rank, m0, n0, (int) threadIdx.x, dry);
-        if (dry) return;
+            cooperative_epilogue<KIND, BN, S, CG, kEpiThreads, CX>(p, vec, data, rank, x_rank, m0, n0, (int) threadIdx.x);
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 8);
         role_sync<(S > 1 || CX == 2), false>();             // nobody leaves while peers still read / share TMEM (execution order only)
         if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 9);
@@ -884,12 +869,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         }
         if (BN >= 256) finish_tile(true);
     }
-    if (BN < 256) {
-        // ONE instance of the epilogue's code, walked twice by the spare warp (dry, then for real) and once by everyone else
-        const int first_pass = (warp == kEpiWarps + 3 && !p.no_warm_epilogue) ? 0 : 1;
-#pragma unroll 1
-        for (int pass = first_pass; pass < 2; pass++) finish_tile(true, pass == 0);
-    }
+    if (BN < 256) finish_tile(true);
 
     if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
@@ -1691,7 +1671,7 @@ mid_kernel(const __grid_constant__ CUtensorMap tm_x1_hi, const __grid_constant__
         gp.out_hi = p.d1_hi; gp.out_lo = p.d1_lo; gp.ld_out = p.ld1;
         gp.a_exp = nullptr; gp.b_exp = nullptr; gp.out_exp = nullptr; gp.aux_exp = nullptr;   // staged in `vec`
         gp.sel_atoms = nullptr; gp.direct_store = 0; gp.dbg = -1; gp.chunk = 1; gp.dry = 0;
-        gp.no_b_prefetch = 0; gp.no_warm_epilogue = 1;
+        gp.no_b_prefetch = 0;
         gp.gsplit = 0; gp.gs_scratch = nullptr; gp.gs_arrive = nullptr; gp.gs_done = nullptr;
         for (int t = rank; t < tiles1; t += CL) {
             drain(nkb2);
@@ -1795,7 +1775,6 @@ struct TensorPlan {
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)
     bool use_mid = false;                           // fused forward / head / backward of the last hidden connection (mid_kernel)
-    bool no_warm_epilogue = false;                  // ANNF_TENSOR_WARM_EPILOGUE=0
     bool no_b_prefetch = false;                     // ANNF_TENSOR_B_PREFETCH=0
     bool no_direct_store = false;                   // ANNF_TENSOR_DIRECT_STORE=0: force tiles leave through the thread epilogue (experiments)
 };
@@ -1900,7 +1879,6 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if (const char* env = getenv("ANNF_GEMM_BN")) t->force_bn = atoi(env);
     if (const char* env = getenv("ANNF_GEMM_SPLIT_SHORTK")) t->force_split = atoi(env);
     if (const char* env = getenv("ANNF_TENSOR_DRY")) t->dry = atoi(env);
-    if (const char* env = getenv("ANNF_TENSOR_WARM_EPILOGUE")) t->no_warm_epilogue = atoi(env) == 0;
     if (const char* env = getenv("ANNF_TENSOR_B_PREFETCH")) t->no_b_prefetch = atoi(env) == 0;
     if (const char* env = getenv("ANNF_TENSOR_DIRECT_STORE")) t->no_direct_store = atoi(env) == 0;
     // fp16 pairs: one K-block (64 values, 12 chained MMAs) per TMEM chunk; TF32 pairs: two (64 values, 24 chained MMAs).
@@ -2133,7 +2111,6 @@ static cudaError_t launch_gemm(TensorPlan* t, PlanSlot* sl, const GemmOp& op_in,
     p.M = R;
     p.dry = t->dry;
     p.no_b_prefetch = t->no_b_prefetch ? 1 : 0;
-    p.no_warm_epilogue = t->no_warm_epilogue ? 1 : 0;
     p.chunk = t->chunk;
     p.dbg = t->dbg_next < 8 ? t->dbg_next++ : -1;
     if (p.epi == EPI_FORCE) {
