@@ -967,7 +967,48 @@ __global__ void __launch_bounds__(256, 7) prep_kernel(NetView net, int R, const 
     const float ref[3] = {__ldg(ref_ptr), __ldg(ref_ptr + 1), __ldg(ref_ptr + 2)};
     float s[3] = {0.f, 0.f, 0.f};
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int g = tid; g < quads; g += nthreads) {
+    // Coalesced walk (contiguous selection, 256 threads): a trip covers 768 consecutive 16-byte vectors, thread t owning vectors
+    // t, t + 256 and t + 512 of it, so a warp's loads and stores are whole 512- / 256-byte runs (whole 32-byte sectors; the
+    // 4-atom groups below touch every sector two or three times: 1.74 M store sectors for 0.58 M of data in
+    // profiles/r02_prep.md).  768 is a multiple of 3, so element i of a thread's m-th vector always has component
+    // (t + m + i) mod 3: statistics and constants are kept ROTATED by t mod 3, which keeps every index static.
+    const bool coalesced = (contiguous & 4) != 0;
+    const int rot = tid % 3, nvec = 3 * quads;
+    if (coalesced) {
+        const float4* src = reinterpret_cast<const float4*>(base);
+        float4* dst = reinterpret_cast<float4*>(xs);
+        const float refl[3] = {ref[rot], ref[(rot + 1) % 3], ref[(rot + 2) % 3]};
+        float sl[3] = {0.f, 0.f, 0.f}, mnl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mxl[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        for (int q0 = tid; q0 < nvec; q0 += 768) {
+            float4 p[3];
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                if (q0 + 256 * m < nvec) p[m] = __ldg(src + q0 + 256 * m);
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                if (q0 + 256 * m < nvec) {
+                    dst[q0 + 256 * m] = p[m];
+                    const float e[4] = {p[m].x, p[m].y, p[m].z, p[m].w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int j = (i + m) % 3;
+                        const float d = e[i] - refl[j];
+                        sl[j] += d;
+                        mnl[j] = fminf(mnl[j], d);
+                        mxl[j] = fmaxf(mxl[j], d);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {                       // rotate back: component c sits at local index (c - rot) mod 3
+            const int j = (c + 3 - rot) % 3;
+            s[c] = j == 0 ? sl[0] : (j == 1 ? sl[1] : sl[2]);
+            mn[c] = j == 0 ? mnl[0] : (j == 1 ? mnl[1] : mnl[2]);
+            mx[c] = j == 0 ? mxl[0] : (j == 1 ? mxl[1] : mxl[2]);
+        }
+    }
+    for (int g = tid; g < quads && !coalesced; g += nthreads) {
         float e[12];
         if (contiguous & 1) {
             // selection is atoms 0..A-1 and rows are 16-byte aligned: three vector loads per 4 atoms
@@ -1025,7 +1066,40 @@ __global__ void __launch_bounds__(256, 7) prep_kernel(NetView net, int R, const 
             chain.x_exp[l + 1][r] = exp_for_bound(b);
         }
     }
-    for (int g = tid; g < quads; g += nthreads) {
+    if (coalesced) {
+        PrepRow rowl = row;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int c = (rot + j) % 3;
+            rowl.ref[j] = c == 0 ? row.ref[0] : (c == 1 ? row.ref[1] : row.ref[2]);
+            rowl.mean[j] = c == 0 ? row.mean[0] : (c == 1 ? row.mean[1] : row.mean[2]);
+        }
+        const float4* src = reinterpret_cast<const float4*>(xs);
+        for (int q0 = tid; q0 < nvec; q0 += 768) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const int q = q0 + 256 * m;
+                if (q < nvec) {
+                    const float4 pv = src[q];
+                    const float4 x = make_float4(prep_feature(rowl, pv.x, m % 3), prep_feature(rowl, pv.y, (m + 1) % 3),
+                                                 prep_feature(rowl, pv.z, (m + 2) % 3), prep_feature(rowl, pv.w, m % 3));
+                    if (KIND == KIND_F16) {
+                        uint2 hi, lo;
+                        split_f16x4(x, hi, lo);
+                        reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld)[q] = hi;
+                        reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld)[q] = lo;
+                    } else {
+                        float hi[4], lo[4];
+                        split_tf32(x.x, hi[0], lo[0]); split_tf32(x.y, hi[1], lo[1]);
+                        split_tf32(x.z, hi[2], lo[2]); split_tf32(x.w, hi[3], lo[3]);
+                        reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld)[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld)[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+        }
+    }
+    for (int g = tid; g < quads && !coalesced; g += nthreads) {
         const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
         const float4 p0 = src[0], p1 = src[1], p2 = src[2];
         const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
@@ -1052,6 +1126,180 @@ __global__ void __launch_bounds__(256, 7) prep_kernel(NetView net, int R, const 
                 for (int j = 0; j < 4; j++) split_tf32(x[4 * q + j], hi[j], lo[j]);
                 oh[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 ol[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
+    ANNF_TGRID_END(dbg);
+}
+
+// prep, one WARP per replica: one-warp CTAs, the row in shared memory (one bulk copy when the selection is contiguous),
+// no block barrier at all — the reductions are warp shuffles and the row's constants live in registers.
+// The one-CTA-per-replica kernel above spends about as many instructions on its per-thread fixed work (prologue, three
+// 32-lane reductions, barrier, constants) as on the 17 elements a thread owns, in each of 8 warps per row, and is
+// instruction-issue bound (ncu: 6.1 M warp-instructions, IPC 0.3 per scheduler, 14.9 us for 18 MB in + 18 MB out); here a lane
+// owns ~140 elements and the fixed work is paid once per row.
+constexpr int kPrepWarps = 1;
+template <int KIND>
+__global__ void __launch_bounds__(32 * kPrepWarps) prep_warp_kernel(NetView net, int R, const float* __restrict__ coords, int N,
+                                                                 void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
+                                                                 ExpChain chain, int dbg) {
+    extern __shared__ __align__(16) float prep_rows[];      // [kPrepWarps][row_floats]
+    __shared__ uint64_t bar[kPrepWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ANNF_TGRID_START(dbg);
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 0);
+    pdl_launch_dependents();
+    if (lane == 0) {
+        ptx::bar_init(ptx::s_u32(&bar[warp]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    pdl_wait();
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
+    const int r = blockIdx.x * kPrepWarps + warp;
+    const int A = net.n_sel, quads = A / 4, row_floats = (3 * A + 3) & ~3;
+    if (r < R) {
+        float* xs = prep_rows + (size_t) warp * row_floats;
+        const float* base = coords + (size_t) r * N * 3;
+        float ref[3] = {0.f, 0.f, 0.f};
+        if (!(contiguous & 1)) {
+            const float* ref_ptr = base + (size_t) net.sel_atoms[0] * 3;
+            ref[0] = __ldg(ref_ptr); ref[1] = __ldg(ref_ptr + 1); ref[2] = __ldg(ref_ptr + 2);
+        }
+        float s[3] = {0.f, 0.f, 0.f};
+        float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        auto stats = [&](const float (&e)[12]) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float d0 = e[c] - ref[c], d1 = e[3 + c] - ref[c], d2 = e[6 + c] - ref[c], d3 = e[9 + c] - ref[c];
+                s[c] += (d0 + d1) + (d2 + d3);
+                mn[c] = fminf(fminf(mn[c], fminf(d0, d1)), fminf(d2, d3));
+                mx[c] = fmaxf(fmaxf(mx[c], fmaxf(d0, d1)), fmaxf(d2, d3));
+            }
+        };
+        if (contiguous & 1) {
+            // the whole row in one bulk copy (TMA engine): a single exposed memory latency per row instead of one per trip
+            if (lane == 0) {
+                ptx::bar_expect_tx(ptx::s_u32(&bar[warp]), (uint32_t) (12 * A));
+                ptx::bulk_load(ptx::s_u32(xs), base, (uint32_t) (12 * A), ptx::s_u32(&bar[warp]));
+            }
+            ptx::bar_wait(ptx::s_u32(&bar[warp]), 0);
+            ref[0] = xs[0]; ref[1] = xs[1]; ref[2] = xs[2];
+            const float4* src = reinterpret_cast<const float4*>(xs);
+            for (int g = lane; g < quads; g += 32) {
+                const float4 p0 = src[3 * g], p1 = src[3 * g + 1], p2 = src[3 * g + 2];
+                const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+                stats(e);
+            }
+        } else {
+            for (int g = lane; g < quads; g += 32) {
+                float e[12];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float* p = base + (size_t) net.sel_atoms[4 * g + k] * 3;
+                    e[3 * k] = __ldg(p); e[3 * k + 1] = __ldg(p + 1); e[3 * k + 2] = __ldg(p + 2);
+                }
+                float4* dst = reinterpret_cast<float4*>(xs) + 3 * g;
+                dst[0] = make_float4(e[0], e[1], e[2], e[3]);
+                dst[1] = make_float4(e[4], e[5], e[6], e[7]);
+                dst[2] = make_float4(e[8], e[9], e[10], e[11]);
+                stats(e);
+            }
+        }
+        // butterfly reductions: every lane ends up with the row's sums, minima and maxima
+        PrepRow row;
+        float bound = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+            }
+            row.ref[c] = ref[c];
+            row.mean[c] = s[c] / (float) A;                 // centroid - p_ref
+            bound = fmaxf(bound, fmaxf(fabsf(mx[c] - row.mean[c]), fabsf(mn[c] - row.mean[c])));
+        }
+        const double inv = 1.0 / net.scale;
+        row.bound = bound * (float) fabs(inv) * 1.000002f;  // head-room for the roundings on the way
+        row.e0 = KIND == KIND_F16 ? exp_for_bound(row.bound) : 0;
+        const double inv_scaled = ldexp(inv, row.e0);
+        row.inv_hi = (float) inv_scaled;
+        row.inv_lo = (float) (inv_scaled - (double) row.inv_hi);
+        if (KIND == KIND_F16 && lane == 0) {
+            chain.x_exp[0][r] = row.e0;
+            float b = row.bound;
+            for (int l = 0; l + 2 < net.L; l++) {            // X_{l+1} = act(W_l X_l + b_l)
+                b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
+                chain.x_exp[l + 1][r] = exp_for_bound(b);
+            }
+        }
+        __syncwarp();                                        // the row buffer was written by other lanes
+        if (contiguous & 1) {
+            // coalesced walk, as in prep_kernel: trips of 96 vectors, lane owning vectors lane, lane + 32, lane + 64 of a trip
+            const int rot = lane % 3, nvec = 3 * quads;
+            PrepRow rowl = row;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int c = (rot + j) % 3;
+                rowl.ref[j] = c == 0 ? row.ref[0] : (c == 1 ? row.ref[1] : row.ref[2]);
+                rowl.mean[j] = c == 0 ? row.mean[0] : (c == 1 ? row.mean[1] : row.mean[2]);
+            }
+            const float4* src = reinterpret_cast<const float4*>(xs);
+            for (int q0 = lane; q0 < nvec; q0 += 96) {
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    const int q = q0 + 32 * m;
+                    if (q < nvec) {
+                        const float4 pv = src[q];
+                        const float4 x = make_float4(prep_feature(rowl, pv.x, (2 * m) % 3), prep_feature(rowl, pv.y, (2 * m + 1) % 3),
+                                                     prep_feature(rowl, pv.z, (2 * m + 2) % 3), prep_feature(rowl, pv.w, (2 * m) % 3));
+                        if (KIND == KIND_F16) {
+                            uint2 hi, lo;
+                            split_f16x4(x, hi, lo);
+                            reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld)[q] = hi;
+                            reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld)[q] = lo;
+                        } else {
+                            float hi[4], lo[4];
+                            split_tf32(x.x, hi[0], lo[0]); split_tf32(x.y, hi[1], lo[1]);
+                            split_tf32(x.z, hi[2], lo[2]); split_tf32(x.w, hi[3], lo[3]);
+                            reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld)[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld)[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                }
+            }
+        }
+        for (int g = lane; g < quads && !(contiguous & 1); g += 32) {
+            const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
+            const float4 p0 = src[0], p1 = src[1], p2 = src[2];
+            const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+            float x[12];
+#pragma unroll
+            for (int j = 0; j < 12; j++) x[j] = prep_feature(row, e[j], j % 3);
+            if (KIND == KIND_F16) {
+                uint2* oh = reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld) + 3 * g;
+                uint2* ol = reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld) + 3 * g;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    uint2 hi, lo;
+                    split_f16x4(make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), hi, lo);
+                    oh[q] = hi;
+                    ol[q] = lo;
+                }
+            } else {
+                float4* oh = reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld) + 3 * g;
+                float4* ol = reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld) + 3 * g;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) split_tf32(x[4 * q + j], hi[j], lo[j]);
+                    oh[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    ol[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
             }
         }
     }
@@ -1771,6 +2019,7 @@ struct TensorPlan {
     int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
+    int prep_mode = 0;                              // ANNF_PREP_MODE: 0 = one CTA per replica, coalesced walk (default); 1 = one warp per replica; 2 = one CTA per replica, 4-atom groups
     bool prep_pipelined = false;                    // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)
@@ -1871,7 +2120,9 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if ((size_t) net.nodes[0] * sizeof(float) > 200 * 1024) return no("input layer too wide for the prep kernel's shared memory");
     if (cudaFuncSetAttribute(prep_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(prep_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(prep_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        cudaFuncSetAttribute(prep_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(prep_warp_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(prep_warp_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return no("cannot configure the prep kernel");
     TensorPlan* t = new TensorPlan();
     t->L = L;
@@ -1939,6 +2190,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     const bool mid_ok = kind == KIND_F16 && L >= 4 && net.nodes[L - 2] <= 128 * kMidCluster && net.nodes[L - 1] <= kMidMaxOut;
     t->use_mid = false;
     if (const char* env = getenv("ANNF_GEMM_GSPLIT")) t->gsplit_mode = atoi(env);
+    if (const char* env = getenv("ANNF_PREP_MODE")) t->prep_mode = atoi(env);
     if (const char* env = getenv("ANNF_PREP_PIPELINED")) t->prep_pipelined = atoi(env) != 0;
     if (const char* env = getenv("ANNF_PREP_THREADS")) t->prep_threads = atoi(env) == 128 ? 128 : 256;
     if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = mid_ok && atoi(env) != 0;
@@ -2295,8 +2547,13 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
         }
         const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
                                (t->dry ? 2 : 0);
+        const int coalesced = (contiguous & 1) && t->prep_threads == 256 && t->prep_mode != 2 ? 4 : 0;
+        const size_t warp_smem = sizeof(float) * kPrepWarps * (size_t) ((t->nodes[0] + 3) & ~3);
+        if (t->prep_mode == 1 && !t->dry && warp_smem <= 200 * 1024)
+            return launch_pdl(prep_warp_kernel<KIND>, dim3((R + kPrepWarps - 1) / kPrepWarps), dim3(32 * kPrepWarps), warp_smem, stream, 1, 0, net, R, coords,
+                              atoms_per_replica, sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain, t->dbg_next++);
         return launch_pdl(prep_kernel<KIND>, dim3(R), dim3(t->prep_threads), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
-                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain, t->dbg_next++);
+                          sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous | coalesced, chain, t->dbg_next++);
     });
     if (err != cudaSuccess) return err;
     const bool mid = KIND == KIND_F16 && t->use_mid;
