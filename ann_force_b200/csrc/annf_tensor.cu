@@ -1133,178 +1133,141 @@ __global__ void __launch_bounds__(256, 7) prep_kernel(NetView net, int R, const 
     ANNF_TGRID_END(dbg);
 }
 
-// prep, one WARP per replica: one-warp CTAs, the row in shared memory (one bulk copy when the selection is contiguous),
-// no block barrier at all — the reductions are warp shuffles and the row's constants live in registers.
-// The one-CTA-per-replica kernel above spends about as many instructions on its per-thread fixed work (prologue, three
-// 32-lane reductions, barrier, constants) as on the 17 elements a thread owns, in each of 8 warps per row, and is
-// instruction-issue bound (ncu: 6.1 M warp-instructions, IPC 0.3 per scheduler, 14.9 us for 18 MB in + 18 MB out); here a lane
-// owns ~140 elements and the fixed work is paid once per row.
-constexpr int kPrepWarps = 1;
-template <int KIND>
-__global__ void __launch_bounds__(32 * kPrepWarps) prep_warp_kernel(NetView net, int R, const float* __restrict__ coords, int N,
-                                                                 void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, int contiguous,
-                                                                 ExpChain chain, int dbg) {
-    extern __shared__ __align__(16) float prep_rows[];      // [kPrepWarps][row_floats]
-    __shared__ uint64_t bar[kPrepWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// prep for a contiguous selection (atoms 0..A-1, 16-byte aligned rows) — the default on that layout.  One CTA of W warps per
+// replica; the whole row of coordinates arrives in shared memory by ONE bulk copy (TMA engine, mbarrier), so a row exposes
+// a single memory latency instead of one per trip of loads, and pass 1 costs no load / store-to-shared instructions at all.
+// W = 1 needs no block barrier (shuffles only) and pays the per-thread fixed work (prologue, reductions, constants: about as
+// many instructions as the 17 elements a thread of prep_kernel owns) once per row instead of eight times; more warps per row
+// shorten the serial chain of one row.  Pass 2 is the coalesced walk of prep_kernel: trips of 3 * T vectors, thread t owning
+// vectors t, t + T, t + 2T of a trip, T = 32 W; element i of the m-th vector has component (t + (T mod 3) m + i) mod 3.
+// Measured at BASELINE C5 (18 MB in, 18 MB out; profiles/r02_prep.md).
+template <int KIND, int W>
+__global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, const float* __restrict__ coords, int N,
+                                                        void* __restrict__ x_hi_v, void* __restrict__ x_lo_v, int ld, ExpChain chain, int dbg) {
+    extern __shared__ __align__(16) float xs[];             // [3 * A]
+    __shared__ uint64_t bar;
+    __shared__ float red[W][9];
+    constexpr int T = 32 * W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x, A = net.n_sel, quads = A / 4, nvec = 3 * quads;
     ANNF_TGRID_START(dbg);
-    if (threadIdx.x == 0) ANNF_TMARK(dbg, 0);
+    if (tid == 0) ANNF_TMARK(dbg, 0);
     pdl_launch_dependents();
-    if (lane == 0) {
-        ptx::bar_init(ptx::s_u32(&bar[warp]), 1);
+    if (tid == 0) {
+        ptx::bar_init(ptx::s_u32(&bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    if (W > 1) __syncthreads(); else __syncwarp();
     pdl_wait();
-    if (threadIdx.x == 0) ANNF_TMARK(dbg, 2);
-    const int r = blockIdx.x * kPrepWarps + warp;
-    const int A = net.n_sel, quads = A / 4, row_floats = (3 * A + 3) & ~3;
-    if (r < R) {
-        float* xs = prep_rows + (size_t) warp * row_floats;
-        const float* base = coords + (size_t) r * N * 3;
-        float ref[3] = {0.f, 0.f, 0.f};
-        if (!(contiguous & 1)) {
-            const float* ref_ptr = base + (size_t) net.sel_atoms[0] * 3;
-            ref[0] = __ldg(ref_ptr); ref[1] = __ldg(ref_ptr + 1); ref[2] = __ldg(ref_ptr + 2);
-        }
-        float s[3] = {0.f, 0.f, 0.f};
-        float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-        auto stats = [&](const float (&e)[12]) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float d0 = e[c] - ref[c], d1 = e[3 + c] - ref[c], d2 = e[6 + c] - ref[c], d3 = e[9 + c] - ref[c];
-                s[c] += (d0 + d1) + (d2 + d3);
-                mn[c] = fminf(fminf(mn[c], fminf(d0, d1)), fminf(d2, d3));
-                mx[c] = fmaxf(fmaxf(mx[c], fmaxf(d0, d1)), fmaxf(d2, d3));
-            }
-        };
-        if (contiguous & 1) {
-            // the whole row in one bulk copy (TMA engine): a single exposed memory latency per row instead of one per trip
-            if (lane == 0) {
-                ptx::bar_expect_tx(ptx::s_u32(&bar[warp]), (uint32_t) (12 * A));
-                ptx::bulk_load(ptx::s_u32(xs), base, (uint32_t) (12 * A), ptx::s_u32(&bar[warp]));
-            }
-            ptx::bar_wait(ptx::s_u32(&bar[warp]), 0);
-            ref[0] = xs[0]; ref[1] = xs[1]; ref[2] = xs[2];
-            const float4* src = reinterpret_cast<const float4*>(xs);
-            for (int g = lane; g < quads; g += 32) {
-                const float4 p0 = src[3 * g], p1 = src[3 * g + 1], p2 = src[3 * g + 2];
-                const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
-                stats(e);
-            }
-        } else {
-            for (int g = lane; g < quads; g += 32) {
-                float e[12];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float* p = base + (size_t) net.sel_atoms[4 * g + k] * 3;
-                    e[3 * k] = __ldg(p); e[3 * k + 1] = __ldg(p + 1); e[3 * k + 2] = __ldg(p + 2);
-                }
-                float4* dst = reinterpret_cast<float4*>(xs) + 3 * g;
-                dst[0] = make_float4(e[0], e[1], e[2], e[3]);
-                dst[1] = make_float4(e[4], e[5], e[6], e[7]);
-                dst[2] = make_float4(e[8], e[9], e[10], e[11]);
-                stats(e);
-            }
-        }
-        // butterfly reductions: every lane ends up with the row's sums, minima and maxima
-        PrepRow row;
-        float bound = 0.f;
+    if (tid == 0) {
+        ANNF_TMARK(dbg, 2);
+        ptx::bar_expect_tx(ptx::s_u32(&bar), (uint32_t) (12 * A));
+        ptx::bulk_load(ptx::s_u32(xs), coords + (size_t) r * N * 3, (uint32_t) (12 * A), ptx::s_u32(&bar));
+    }
+    ptx::bar_wait(ptx::s_u32(&bar), 0);
+    const float ref[3] = {xs[0], xs[1], xs[2]};
+    float s[3] = {0.f, 0.f, 0.f};
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int g = tid; g < quads; g += T) {                  // 4 atoms = 3 vectors, 48-byte stride: conflict-free shared loads
+        const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
+        const float4 p0 = src[0], p1 = src[1], p2 = src[2];
+        const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
-                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
-                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
-            }
-            row.ref[c] = ref[c];
-            row.mean[c] = s[c] / (float) A;                 // centroid - p_ref
-            bound = fmaxf(bound, fmaxf(fabsf(mx[c] - row.mean[c]), fabsf(mn[c] - row.mean[c])));
+            const float d0 = e[c] - ref[c], d1 = e[3 + c] - ref[c], d2 = e[6 + c] - ref[c], d3 = e[9 + c] - ref[c];
+            s[c] += (d0 + d1) + (d2 + d3);
+            mn[c] = fminf(fminf(mn[c], fminf(d0, d1)), fminf(d2, d3));
+            mx[c] = fmaxf(fmaxf(mx[c], fmaxf(d0, d1)), fmaxf(d2, d3));
         }
-        const double inv = 1.0 / net.scale;
-        row.bound = bound * (float) fabs(inv) * 1.000002f;  // head-room for the roundings on the way
-        row.e0 = KIND == KIND_F16 ? exp_for_bound(row.bound) : 0;
-        const double inv_scaled = ldexp(inv, row.e0);
-        row.inv_hi = (float) inv_scaled;
-        row.inv_lo = (float) (inv_scaled - (double) row.inv_hi);
-        if (KIND == KIND_F16 && lane == 0) {
-            chain.x_exp[0][r] = row.e0;
-            float b = row.bound;
-            for (int l = 0; l + 2 < net.L; l++) {            // X_{l+1} = act(W_l X_l + b_l)
-                b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
-                chain.x_exp[l + 1][r] = exp_for_bound(b);
-            }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {                           // butterflies: every lane ends up with the warp's sums, minima, maxima
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
         }
-        __syncwarp();                                        // the row buffer was written by other lanes
-        if (contiguous & 1) {
-            // coalesced walk, as in prep_kernel: trips of 96 vectors, lane owning vectors lane, lane + 32, lane + 64 of a trip
-            const int rot = lane % 3, nvec = 3 * quads;
-            PrepRow rowl = row;
+    }
+    if (W > 1) {
+        if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const int c = (rot + j) % 3;
-                rowl.ref[j] = c == 0 ? row.ref[0] : (c == 1 ? row.ref[1] : row.ref[2]);
-                rowl.mean[j] = c == 0 ? row.mean[0] : (c == 1 ? row.mean[1] : row.mean[2]);
-            }
-            const float4* src = reinterpret_cast<const float4*>(xs);
-            for (int q0 = lane; q0 < nvec; q0 += 96) {
-#pragma unroll
-                for (int m = 0; m < 3; m++) {
-                    const int q = q0 + 32 * m;
-                    if (q < nvec) {
-                        const float4 pv = src[q];
-                        const float4 x = make_float4(prep_feature(rowl, pv.x, (2 * m) % 3), prep_feature(rowl, pv.y, (2 * m + 1) % 3),
-                                                     prep_feature(rowl, pv.z, (2 * m + 2) % 3), prep_feature(rowl, pv.w, (2 * m) % 3));
-                        if (KIND == KIND_F16) {
-                            uint2 hi, lo;
-                            split_f16x4(x, hi, lo);
-                            reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld)[q] = hi;
-                            reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld)[q] = lo;
-                        } else {
-                            float hi[4], lo[4];
-                            split_tf32(x.x, hi[0], lo[0]); split_tf32(x.y, hi[1], lo[1]);
-                            split_tf32(x.z, hi[2], lo[2]); split_tf32(x.w, hi[3], lo[3]);
-                            reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld)[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                            reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld)[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        }
-                    }
-                }
-            }
+            for (int c = 0; c < 3; c++) { red[warp][c] = s[c]; red[warp][3 + c] = mn[c]; red[warp][6 + c] = mx[c]; }
         }
-        for (int g = lane; g < quads && !(contiguous & 1); g += 32) {
-            const float4* src = reinterpret_cast<const float4*>(xs) + 3 * g;
-            const float4 p0 = src[0], p1 = src[1], p2 = src[2];
-            const float e[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
-            float x[12];
+        __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 12; j++) x[j] = prep_feature(row, e[j], j % 3);
-            if (KIND == KIND_F16) {
-                uint2* oh = reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld) + 3 * g;
-                uint2* ol = reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld) + 3 * g;
+        for (int c = 0; c < 3; c++) {
+            s[c] = red[0][c]; mn[c] = red[0][3 + c]; mx[c] = red[0][6 + c];
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+            for (int w = 1; w < W; w++) { s[c] += red[w][c]; mn[c] = fminf(mn[c], red[w][3 + c]); mx[c] = fmaxf(mx[c], red[w][6 + c]); }
+        }
+    }
+    PrepRow row;
+    float bound = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        row.ref[c] = ref[c];
+        row.mean[c] = s[c] / (float) A;                     // centroid - p_ref
+        bound = fmaxf(bound, fmaxf(fabsf(mx[c] - row.mean[c]), fabsf(mn[c] - row.mean[c])));
+    }
+    const double inv = 1.0 / net.scale;
+    row.bound = bound * (float) fabs(inv) * 1.000002f;      // head-room for the roundings on the way
+    row.e0 = KIND == KIND_F16 ? exp_for_bound(row.bound) : 0;
+    const double inv_scaled = ldexp(inv, row.e0);
+    row.inv_hi = (float) inv_scaled;
+    row.inv_lo = (float) (inv_scaled - (double) row.inv_hi);
+    if (KIND == KIND_F16 && tid == 0) {
+        chain.x_exp[0][r] = row.e0;
+        float b = row.bound;
+        for (int l = 0; l + 2 < net.L; l++) {                // X_{l+1} = act(W_l X_l + b_l)
+            b = net.types[l] == ANNF_TANH ? 1.f : chain.fwd_bias[l] + b * chain.fwd_gain[l];
+            chain.x_exp[l + 1][r] = exp_for_bound(b);
+        }
+    }
+    const int rot = tid % 3;
+    PrepRow rowl = row;                                     // constants rotated so that local index j means component (rot + j) mod 3
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int c = (rot + j) % 3;
+        rowl.ref[j] = c == 0 ? row.ref[0] : (c == 1 ? row.ref[1] : row.ref[2]);
+        rowl.mean[j] = c == 0 ? row.mean[0] : (c == 1 ? row.mean[1] : row.mean[2]);
+    }
+    const float4* src = reinterpret_cast<const float4*>(xs);
+    for (int q0 = tid; q0 < nvec; q0 += 3 * T) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const int q = q0 + T * m;
+            constexpr int step = T % 3;
+            if (q < nvec) {
+                const float4 pv = src[q];
+                const float4 x = make_float4(prep_feature(rowl, pv.x, (step * m) % 3), prep_feature(rowl, pv.y, (step * m + 1) % 3),
+                                             prep_feature(rowl, pv.z, (step * m + 2) % 3), prep_feature(rowl, pv.w, (step * m) % 3));
+                if (KIND == KIND_F16) {
                     uint2 hi, lo;
-                    split_f16x4(make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), hi, lo);
-                    oh[q] = hi;
-                    ol[q] = lo;
-                }
-            } else {
-                float4* oh = reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld) + 3 * g;
-                float4* ol = reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld) + 3 * g;
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
+                    split_f16x4(x, hi, lo);
+                    reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld)[q] = hi;
+                    reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld)[q] = lo;
+                } else {
                     float hi[4], lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) split_tf32(x[4 * q + j], hi[j], lo[j]);
-                    oh[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    ol[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    split_tf32(x.x, hi[0], lo[0]); split_tf32(x.y, hi[1], lo[1]);
+                    split_tf32(x.z, hi[2], lo[2]); split_tf32(x.w, hi[3], lo[3]);
+                    reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld)[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld)[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         }
     }
-    if (threadIdx.x == 0) ANNF_TMARK(dbg, 9);
+    if (tid == 0) ANNF_TMARK(dbg, 9);
     ANNF_TGRID_END(dbg);
+}
+
+template <int KIND>
+static bool prep_bulk_attributes() {
+    const int bytes = 200 * 1024;
+    return cudaFuncSetAttribute(prep_bulk_kernel<KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+           cudaFuncSetAttribute(prep_bulk_kernel<KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+           cudaFuncSetAttribute(prep_bulk_kernel<KIND, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+           cudaFuncSetAttribute(prep_bulk_kernel<KIND, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
 }
 
 // prep, persistent flavour (KIND_F16, selection = atoms 0..A-1, 16-byte aligned rows): 2 CTAs per SM walk the replicas; the
@@ -2019,7 +1982,8 @@ struct TensorPlan {
     int dbg_next = 0;                               // diagnostic builds: g_tensor_clock slot of the next launch of the step
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
-    int prep_mode = 0;                              // ANNF_PREP_MODE: 0 = one CTA per replica, coalesced walk (default); 1 = one warp per replica; 2 = one CTA per replica, 4-atom groups
+    int prep_mode = 0;                              // ANNF_PREP_MODE: 0 = bulk-copy kernel when the selection is contiguous (default); 1 = prep_kernel, coalesced walk; 2 = prep_kernel, 4-atom groups
+    int prep_warps = 4;                             // ANNF_PREP_WARPS: warps per replica of the bulk-copy kernel (1, 2, 4, 8)
     bool prep_pipelined = false;                    // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)
@@ -2121,8 +2085,7 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     if (cudaFuncSetAttribute(prep_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(prep_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(prep_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(prep_warp_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(prep_warp_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        !prep_bulk_attributes<KIND_TF32>() || !prep_bulk_attributes<KIND_F16>())
         return no("cannot configure the prep kernel");
     TensorPlan* t = new TensorPlan();
     t->L = L;
@@ -2191,6 +2154,10 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     t->use_mid = false;
     if (const char* env = getenv("ANNF_GEMM_GSPLIT")) t->gsplit_mode = atoi(env);
     if (const char* env = getenv("ANNF_PREP_MODE")) t->prep_mode = atoi(env);
+    if (const char* env = getenv("ANNF_PREP_WARPS")) {
+        const int w = atoi(env);
+        if (w == 1 || w == 2 || w == 4 || w == 8) t->prep_warps = w;
+    }
     if (const char* env = getenv("ANNF_PREP_PIPELINED")) t->prep_pipelined = atoi(env) != 0;
     if (const char* env = getenv("ANNF_PREP_THREADS")) t->prep_threads = atoi(env) == 128 ? 128 : 256;
     if (const char* env = getenv("ANNF_TENSOR_MID")) t->use_mid = mid_ok && atoi(env) != 0;
@@ -2548,10 +2515,17 @@ static cudaError_t plan_run_t(TensorPlan* t, Profiler* prof, const NetView& net,
         const int contiguous = (t->sel_identity && (3 * atoms_per_replica) % 4 == 0 && (reinterpret_cast<uintptr_t>(coords) & 15) == 0 ? 1 : 0) |
                                (t->dry ? 2 : 0);
         const int coalesced = (contiguous & 1) && t->prep_threads == 256 && t->prep_mode != 2 ? 4 : 0;
-        const size_t warp_smem = sizeof(float) * kPrepWarps * (size_t) ((t->nodes[0] + 3) & ~3);
-        if (t->prep_mode == 1 && !t->dry && warp_smem <= 200 * 1024)
-            return launch_pdl(prep_warp_kernel<KIND>, dim3((R + kPrepWarps - 1) / kPrepWarps), dim3(32 * kPrepWarps), warp_smem, stream, 1, 0, net, R, coords,
-                              atoms_per_replica, sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous, chain, t->dbg_next++);
+        const size_t row_smem = sizeof(float) * (size_t) t->nodes[0];
+        if (t->prep_mode == 0 && (contiguous & 1) && !t->dry && row_smem <= 200 * 1024) {
+            auto bulk = [&](auto kernel, int warps) {
+                return launch_pdl(kernel, dim3(R), dim3(32 * warps), row_smem, stream, 1, 0, net, R, coords, atoms_per_replica, sl->x_hi[0], sl->x_lo[0],
+                                  t->ld[0], chain, t->dbg_next++);
+            };
+            if (t->prep_warps == 1) return bulk(prep_bulk_kernel<KIND, 1>, 1);
+            if (t->prep_warps == 2) return bulk(prep_bulk_kernel<KIND, 2>, 2);
+            if (t->prep_warps == 4) return bulk(prep_bulk_kernel<KIND, 4>, 4);
+            return bulk(prep_bulk_kernel<KIND, 8>, 8);
+        }
         return launch_pdl(prep_kernel<KIND>, dim3(R), dim3(t->prep_threads), sizeof(float) * t->nodes[0], stream, 1, 0, net, R, coords, atoms_per_replica,
                           sl->x_hi[0], sl->x_lo[0], t->ld[0], contiguous | coalesced, chain, t->dbg_next++);
     });

@@ -545,6 +545,28 @@ def test_split_k_through_global_memory(splits, precision, monkeypatch):
     assert max_norm_rel(runs[0][1], f_ref) <= F_RTOL
 
 
+@pytest.mark.parametrize("precision", TENSOR_KINDS)
+@pytest.mark.parametrize("mode", ["0/1", "0/2", "0/4", "0/8", "1/1", "2/1"])
+@pytest.mark.parametrize("atoms", [400, 404, 1500])
+def test_prep_kernel_flavours_agree(atoms, mode, precision, monkeypatch):
+    """The ways the coordinate rows are centred, scaled and split (ANNF_PREP_MODE / ANNF_PREP_WARPS: 0 = one bulk copy per
+    replica into shared memory, 1 - 8 warps per replica — the default with 4; 1 = loads by 256 threads per replica, 16-byte
+    vectors with rotated statistics; 2 = the same kernel walking 4-atom groups) against the oracle, on a molecule 40 nm from
+    the origin (the arithmetic is relative to the replica's first atom) and on row lengths that end a trip of the vector
+    walk at different points."""
+    monkeypatch.setenv("ANNF_PREP_MODE", mode.split("/")[0])
+    monkeypatch.setenv("ANNF_PREP_WARPS", mode.split("/")[1])
+    nodes, types, R = [3 * atoms, 512, 256, 4], ["Tanh", "Tanh", "Tanh"], 130
+    force = synthetic.make_force(nodes, types, atoms, seed=71)
+    pos = synthetic.make_positions(atoms, R, seed=72) + np.float32(40.0)
+    cen = synthetic.make_centers(force, R, seed=73)
+    e, f, _ = run_batched(force, pos, cen, precision=precision)
+    e_ref, f_ref = port.evaluate(force, pos.astype(np.float64), cen.astype(np.float64))
+    scale = np.maximum(np.abs(e_ref), np.median(np.abs(e_ref)))
+    assert np.max(np.abs(e - e_ref) / scale) <= 2e-5
+    assert max_norm_rel(f, f_ref) <= F_RTOL
+
+
 def test_fused_middle_kernel_matches_the_three_kernel_path(monkeypatch):
     """f16x3 with the last hidden connection + head + its backward in ONE kernel (ANNF_TENSOR_MID=1) against the same step as
     GEMM, head kernel, GEMM (the default): same arithmetic except for the order of the output-layer partial sums, so the
