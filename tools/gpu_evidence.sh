@@ -10,6 +10,11 @@ for i in 1 2 3; do echo "== bench k20 #$i"; timeout -k 10 600 python bench.py --
 echo "== bench default"; timeout -k 10 600 python bench.py > $O/ev_bench_default.json 2> $O/ev_bench_default.err
 for w in c2 c3 c4; do echo "== bench $w"; timeout -k 10 300 python bench.py --workload $w > $O/ev_bench_$w.json 2> $O/ev_bench_$w.err; done
 echo "== bench c5 tf32x3"; timeout -k 10 300 python bench.py --precision tf32x3 --no-others --no-cpu-baseline > $O/ev_bench_c5_tf32x3.json 2> $O/ev_bench_c5_tf32x3.err
+echo "== prep flavours"
+for spec in "0 1" "0 2" "0 4" "0 8" "1 4" "2 4"; do set -- $spec
+  echo "mode $1 warps $2: $(ANNF_PREP_MODE=$1 ANNF_PREP_WARPS=$2 timeout -k 10 300 python bench.py --steps 20 --warmup 5 --no-others --no-cpu-baseline --no-parity 2>/dev/null | python -c 'import json,sys; print(json.load(sys.stdin)["ms_per_step"])')"
+done > $O/ev_prep_flavours.txt 2>&1; cat $O/ev_prep_flavours.txt
+echo "== two streams"; timeout -k 10 300 python tools/two_stream_probe.py --replicas 1024 > $O/ev_two_stream.txt 2>&1; timeout -k 10 300 python tools/two_stream_probe.py --replicas 2048 >> $O/ev_two_stream.txt 2>&1; cat $O/ev_two_stream.txt
 echo "== launch list"
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_c5.csv python bench.py --no-others --no-cpu-baseline --no-parity --steps 20 --warmup 3 --graph off --e2e-steps 1 > $O/ev_ncu_launch.log 2>&1
 echo "== ncu full (one step)"
