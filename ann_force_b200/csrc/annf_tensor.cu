@@ -838,6 +838,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             // 16-byte unit index is XORed with row % 8, so the 32 lanes of a store hit every bank exactly four times), and ONE
             // thread hands the boxes to the TMA engine.  The thread-per-group store loop this replaces was latency-bound:
             // 10.8 us for 18 MB at BASELINE C5 (profiles/r02_c5_phases.md).  Rows >= M and columns >= N are clipped by the TMA unit.
+            if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 11);
             const int ea = KIND == KIND_F16 ? s_a_exp[row] : 0;
             unsigned char* dst = data + (size_t) row * 128;
 #pragma unroll
@@ -853,9 +854,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             fence_proxy_async_smem();                                              // generic-proxy writes -> visible to the TMA engine
             asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
             if (threadIdx.x == 0) {
+                ANNF_TMARK(p.dbg, 12);
                 for (int cb = 0; cb < BN / 32; cb++)
                     if (n0 + cb * 32 < p.N) tma_store_2d(&tm_out, smem_u32(data + (size_t) cb * (BM * 128)), n0 + cb * 32, m0);
+                ANNF_TMARK(p.dbg, 13);
                 tma_store_commit_and_wait_read();                                  // shared memory has been read: the CTA may leave
+                ANNF_TMARK(p.dbg, 14);
             }
         } else {
             // park the tile in shared memory (all TMA loads have landed and been consumed: the stage buffers are free).

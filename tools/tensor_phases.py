@@ -32,7 +32,7 @@ for i in range(16):
     k.execute_batched(coords[i % 8], cen, out[i % 8], en)
 torch.cuda.synchronize()
 names = ["k0", "k1", "k2", "k3", "k4", "k5", "k6", "k7"]   # launch order: prep, forward GEMMs, (fused middle | GEMM, head, GEMM), backward GEMMs
-phase = ["entry", "prologue", "deps", "tma0", "landed0", "mma_done", "drained", "parked", "epilogue", "exit", "p10", "p11", "p12", "p13", "p14", "p15"]
+phase = ["entry", "prologue", "deps", "tma0", "landed0", "mma_done", "drained", "parked", "epilogue", "exit", "p10", "vectors", "staged", "stores_issued", "stores_read", "p15"]
 buf = (C.c_int64 * 192)()
 for rep in range(3):
     _capi.check(_capi.lib().annf_debug_tensor_phases(k._handle, buf, 1))
