@@ -126,10 +126,64 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// L2 eviction priorities (compile-time: -DANNF_L2_HINTS=mask, default 7).  A step streams 18 MB of coordinates in and 18 MB of
+// forces out through an L2 that also has to keep 18 MB of weights and the 18 MB operand pair prep rewrites in place every step;
+// with default priorities the streams push those out (steady state, ncu --cache-control none: 13 MB of weights re-read from
+// DRAM and 15 MB of dead operand rows written back per step; profiles/r02_l2_hints.md).
+//   bit 0  coordinates in: evict_first          bit 2  operand pairs (plan buffers, rewritten every step): evict_last
+//   bit 1  forces out: evict_first              bit 3  weights: evict_last
+// The unhinted instruction is used where a bit is off: a created evict_normal policy is NOT the default (hinting every access
+// "normal" cost the C5 step 4 us), and a run-time choice between the two forms cost 1.6 us (branches in prep's store loop).
+#ifndef ANNF_L2_HINTS
+#define ANNF_L2_HINTS 7
+#endif
+constexpr int kL2Hints = ANNF_L2_HINTS;
+__device__ __forceinline__ uint64_t l2_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool HINT>
+__device__ __forceinline__ void bulk_load_h(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    if (HINT)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
+template <bool HINT>
+__device__ __forceinline__ void st_v2_h(uint2* ptr, uint2 v, uint64_t pol) {
+    if (HINT) asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(ptr), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+    else *ptr = v;
+}
+template <bool HINT>
+__device__ __forceinline__ void st_v4_h(float4* ptr, float4 v, uint64_t pol) {
+    if (HINT) asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+    else *ptr = v;
+}
+template <bool HINT>
+__device__ __forceinline__ void tma_load_2d_h(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+    if (HINT)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+    else tma_load_2d(dst, map, bar, c0, c1);
+}
 // shared -> global tile store by the TMA engine (bulk async-group completion)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+template <bool HINT>
+__device__ __forceinline__ void tma_store_2d_h(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t pol) {
+    if (HINT)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                     ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -257,10 +311,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; completes its bytes on the mbarrier at `bar_cluster` (the leader's)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+template <bool HINT>
+__device__ __forceinline__ void tma_load_2d_pair_h(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, uint64_t pol) {
+    if (HINT)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(pol) : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
 }
 template <int KIND>
 __device__ __forceinline__ void umma_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -292,10 +352,16 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
 }
 // TMA load whose box lands at the same shared-memory offset, and completes its bytes on the mbarrier at the same offset, in
 // every CTA of `cta_mask`
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+template <bool HINT>
+__device__ __forceinline__ void tma_load_2d_mc_h(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask, uint64_t pol) {
+    if (HINT)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(pol) : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
 }
 // a / b format field: kind::tf32 -> 2 (TF32); kind::f16 -> 0 (F16)
 __host__ __device__ constexpr uint32_t umma_idesc_mn(int kind, int m, int n) {
@@ -602,6 +668,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 1);
     // One pipeline stage of K-block i: arm the stage's barrier, load the A rows (activations: written by the kernel before this
     // one) and / or the B rows (weights: static).  Called by the producer thread only.
+    constexpr bool kHintA = (kL2Hints & 4) != 0, kHintB = (kL2Hints & 8) != 0;
+    const uint64_t pol_last = (kHintA || kHintB) ? l2_evict_last() : 0;
     auto issue_stage = [&](int i, bool do_a, bool do_b, bool arm) {
         const int s = i % kStages;
         const uint32_t full = smem_u32(&bar_full[s]);
@@ -614,14 +682,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 else mbar_arrive_cluster(full_leader);
             }
             if (do_a) {
-                tma_load_2d_pair(base, &tm_a_hi, full_leader, kc, m0);
-                tma_load_2d_pair(base + BM * kBlockBytes, &tm_a_lo, full_leader, kc, m0);
+                tma_load_2d_pair_h<kHintA>(base, &tm_a_hi, full_leader, kc, m0, pol_last);
+                tma_load_2d_pair_h<kHintA>(base + BM * kBlockBytes, &tm_a_lo, full_leader, kc, m0, pol_last);
             }
             if (do_b) {
 #pragma unroll
                 for (int h = 0; h < kBRows / kBBox; h++) {
-                    tma_load_2d_pair(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox);
-                    tma_load_2d_pair(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox);
+                    tma_load_2d_pair_h<kHintB>(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full_leader, kc, b_row0 + h * kBBox, pol_last);
+                    tma_load_2d_pair_h<kHintB>(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full_leader, kc, b_row0 + h * kBBox, pol_last);
                 }
             }
         } else {
@@ -630,18 +698,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 if (NX == 2) {
                     // own half of the A rows to both CTAs (the maps have 64-row boxes); the other half arrives from the peer
                     const uint32_t half = (uint32_t) x_rank * (BM / 2) * kBlockBytes;
-                    tma_load_2d_mc(base + half, &tm_a_hi, full, kc, m0 + x_rank * (BM / 2), mc_mask);
-                    tma_load_2d_mc(base + BM * kBlockBytes + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask);
+                    tma_load_2d_mc_h<kHintA>(base + half, &tm_a_hi, full, kc, m0 + x_rank * (BM / 2), mc_mask, pol_last);
+                    tma_load_2d_mc_h<kHintA>(base + BM * kBlockBytes + half, &tm_a_lo, full, kc, m0 + x_rank * (BM / 2), mc_mask, pol_last);
                 } else {
-                    tma_load_2d(base, &tm_a_hi, full, kc, m0);
-                    tma_load_2d(base + BM * kBlockBytes, &tm_a_lo, full, kc, m0);
+                    tma_load_2d_h<kHintA>(base, &tm_a_hi, full, kc, m0, pol_last);
+                    tma_load_2d_h<kHintA>(base + BM * kBlockBytes, &tm_a_lo, full, kc, m0, pol_last);
                 }
             }
             if (do_b) {
 #pragma unroll
                 for (int h = 0; h < kBRows / kBBox; h++) {                        // TMA boxes are at most 256 rows; use 128-row boxes
-                    tma_load_2d(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox);
-                    tma_load_2d(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox);
+                    tma_load_2d_h<kHintB>(base + 2 * BM * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_hi, full, kc, b_row0 + h * kBBox, pol_last);
+                    tma_load_2d_h<kHintB>(base + 2 * BM * kBlockBytes + kBRows * kBlockBytes + h * kBBox * kBlockBytes, &tm_b_lo, full, kc, b_row0 + h * kBBox, pol_last);
                 }
             }
         }
@@ -855,8 +923,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
             if (threadIdx.x == 0) {
                 ANNF_TMARK(p.dbg, 12);
+                const uint64_t pol_out = (kL2Hints & 2) ? l2_evict_first() : 0;
                 for (int cb = 0; cb < BN / 32; cb++)
-                    if (n0 + cb * 32 < p.N) tma_store_2d(&tm_out, smem_u32(data + (size_t) cb * (BM * 128)), n0 + cb * 32, m0);
+                    if (n0 + cb * 32 < p.N) tma_store_2d_h<(kL2Hints & 2) != 0>(&tm_out, smem_u32(data + (size_t) cb * (BM * 128)), n0 + cb * 32, m0, pol_out);
                 ANNF_TMARK(p.dbg, 13);
                 tma_store_commit_and_wait_read();                                  // shared memory has been read: the CTA may leave
                 ANNF_TMARK(p.dbg, 14);
@@ -896,13 +965,29 @@ struct ExpChain {
     float bwd_gain[kMaxLayers];     // max_i sum_j |W_l[j][i]|       (connection l, backward)
     int* x_exp[kMaxLayers];         // [R] per forward tensor X_l, l = 0..L-2   (written by prep)
     int* d_exp[kMaxLayers];         // [R] per gradient tensor D_l, l = 1..L-2  (written by head)
+    double inv_scale;               // 1 / scaling_factor (a double division per thread of prep otherwise)
+    float inv_hi, inv_lo;           // the same as a float pair: hi = fl(1/s), lo = fl(1/s - hi); scaling by 2^e keeps the pair exact
 };
 
 __device__ __forceinline__ int exp_for_bound(float bound) {
     if (!(bound > 0.f) || !(bound < 3.0e38f)) return 0;
-    int q;
-    frexpf(bound, &q);                                      // bound = f * 2^q, 0.5 <= f < 1
+    // bound = f * 2^q with 0.5 <= f < 1: q = biased exponent - 126.  (A subnormal bound reads q = -126 instead of its true,
+    // smaller q: both end at the upper clamp.)
+    const int q = (int) ((__float_as_uint(bound) >> 23) & 0xffu) - 126;
     return max(-kExpClamp, min(kExpClamp, kExpTarget - q));
+}
+// warp-wide min / max of floats by one integer redux.sync: key(x) is monotonic in x (sign-magnitude -> two's-complement order)
+__device__ __forceinline__ float warp_min_float(float v) {
+    const int b = __float_as_int(v);
+    const int key = b >= 0 ? b : (int) (0x80000000u - (unsigned) b);
+    const int r = __reduce_min_sync(0xffffffffu, key);
+    return __int_as_float(r >= 0 ? r : (int) (0x80000000u - (unsigned) r));
+}
+__device__ __forceinline__ float warp_max_float(float v) {
+    const int b = __float_as_int(v);
+    const int key = b >= 0 ? b : (int) (0x80000000u - (unsigned) b);
+    const int r = __reduce_max_sync(0xffffffffu, key);
+    return __int_as_float(r >= 0 ? r : (int) (0x80000000u - (unsigned) r));
 }
 
 // prep: gather + scale + remove centroid (ANN_ReferenceKernels.cpp:128-151), write the operand pair.
@@ -1166,9 +1251,11 @@ __global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, c
     if (tid == 0) {
         ANNF_TMARK(dbg, 2);
         ptx::bar_expect_tx(ptx::s_u32(&bar), (uint32_t) (12 * A));
-        ptx::bulk_load(ptx::s_u32(xs), coords + (size_t) r * N * 3, (uint32_t) (12 * A), ptx::s_u32(&bar));
+        // the coordinates are read once (evict_first); the operand pair is rewritten in place every step (evict_last)
+        bulk_load_h<(kL2Hints & 1) != 0>(ptx::s_u32(xs), coords + (size_t) r * N * 3, (uint32_t) (12 * A), ptx::s_u32(&bar), (kL2Hints & 1) ? l2_evict_first() : 0);
     }
     ptx::bar_wait(ptx::s_u32(&bar), 0);
+    if (tid == 0) ANNF_TMARK(dbg, 3);
     const float ref[3] = {xs[0], xs[1], xs[2]};
     float s[3] = {0.f, 0.f, 0.f};
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -1185,13 +1272,11 @@ __global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, c
         }
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) {                           // butterflies: every lane ends up with the warp's sums, minima, maxima
+    for (int c = 0; c < 3; c++) {                           // every lane ends up with the warp's sums, minima, maxima
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
-            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
-            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
-        }
+        for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+        mn[c] = warp_min_float(mn[c]);                      // one redux.sync each on order-preserving integer keys
+        mx[c] = warp_max_float(mx[c]);
     }
     if (W > 1) {
         if (lane == 0) {
@@ -1214,12 +1299,10 @@ __global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, c
         row.mean[c] = s[c] / (float) A;                     // centroid - p_ref
         bound = fmaxf(bound, fmaxf(fabsf(mx[c] - row.mean[c]), fabsf(mn[c] - row.mean[c])));
     }
-    const double inv = 1.0 / net.scale;
-    row.bound = bound * (float) fabs(inv) * 1.000002f;      // head-room for the roundings on the way
+    row.bound = bound * fabsf(chain.inv_hi) * 1.000002f;    // head-room for the roundings on the way
     row.e0 = KIND == KIND_F16 ? exp_for_bound(row.bound) : 0;
-    const double inv_scaled = ldexp(inv, row.e0);
-    row.inv_hi = (float) inv_scaled;
-    row.inv_lo = (float) (inv_scaled - (double) row.inv_hi);
+    row.inv_hi = chain.inv_hi * exp2i(row.e0);              // |e0| <= 60: exact
+    row.inv_lo = chain.inv_lo * exp2i(row.e0);
     if (KIND == KIND_F16 && tid == 0) {
         chain.x_exp[0][r] = row.e0;
         float b = row.bound;
@@ -1228,6 +1311,7 @@ __global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, c
             chain.x_exp[l + 1][r] = exp_for_bound(b);
         }
     }
+    if (tid == 0) ANNF_TMARK(dbg, 4);
     const int rot = tid % 3;
     PrepRow rowl = row;                                     // constants rotated so that local index j means component (rot + j) mod 3
 #pragma unroll
@@ -1237,6 +1321,8 @@ __global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, c
         rowl.mean[j] = c == 0 ? row.mean[0] : (c == 1 ? row.mean[1] : row.mean[2]);
     }
     const float4* src = reinterpret_cast<const float4*>(xs);
+    constexpr bool kHintX = (kL2Hints & 4) != 0;
+    const uint64_t pol_x = kHintX ? l2_evict_last() : 0;
     for (int q0 = tid; q0 < nvec; q0 += 3 * T) {
 #pragma unroll
         for (int m = 0; m < 3; m++) {
@@ -1249,14 +1335,14 @@ __global__ void __launch_bounds__(32 * W) prep_bulk_kernel(NetView net, int R, c
                 if (KIND == KIND_F16) {
                     uint2 hi, lo;
                     split_f16x4(x, hi, lo);
-                    reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld)[q] = hi;
-                    reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld)[q] = lo;
+                    st_v2_h<kHintX>(reinterpret_cast<uint2*>(static_cast<__half*>(x_hi_v) + (size_t) r * ld) + q, hi, pol_x);
+                    st_v2_h<kHintX>(reinterpret_cast<uint2*>(static_cast<__half*>(x_lo_v) + (size_t) r * ld) + q, lo, pol_x);
                 } else {
                     float hi[4], lo[4];
                     split_tf32(x.x, hi[0], lo[0]); split_tf32(x.y, hi[1], lo[1]);
                     split_tf32(x.z, hi[2], lo[2]); split_tf32(x.w, hi[3], lo[3]);
-                    reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld)[q] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld)[q] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    st_v4_h<kHintX>(reinterpret_cast<float4*>(static_cast<float*>(x_hi_v) + (size_t) r * ld) + q, make_float4(hi[0], hi[1], hi[2], hi[3]), pol_x);
+                    st_v4_h<kHintX>(reinterpret_cast<float4*>(static_cast<float*>(x_lo_v) + (size_t) r * ld) + q, make_float4(lo[0], lo[1], lo[2], lo[3]), pol_x);
                 }
             }
         }
@@ -2110,6 +2196,9 @@ TensorPlan* tensor_plan_create(const NetView& net, const std::vector<std::vector
     const int ld_unit = kind == KIND_F16 ? 8 : 4;               // rows are 16-byte multiples (TMA global stride)
     for (int l = 0; l < L; l++) { t->nodes[l] = net.nodes[l]; t->ld[l] = round_up(net.nodes[l], ld_unit); }
     for (int l = 0; l + 1 < L; l++) t->types[l] = net.types[l];
+    t->chain.inv_scale = 1.0 / net.scale;
+    t->chain.inv_hi = (float) t->chain.inv_scale;
+    t->chain.inv_lo = (float) (t->chain.inv_scale - (double) t->chain.inv_hi);
     // norms for the magnitude bounds of KIND_F16 (ExpChain): forward max row L1 norm and max |bias|, backward max column L1 norm
     for (int l = 0; l + 1 < L; l++) {
         const int n_in = net.nodes[l], n_out = net.nodes[l + 1];
