@@ -286,12 +286,27 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define ANNF_TGRID_END(slot) do { if ((slot) >= 0 && threadIdx.x == 0) atomicMax(&g_tensor_clock[slot][18], gtimer()); } while (0)
 // SM cycles CTA 0's single-thread roles spent waiting: [19] MMA issuer on accumulator buffers, [20] MMA issuer on operands,
 // [21] TMA producer on free stages, [22] epilogue warp 0 on finished chunks
+// per-CTA marks of the GEMM launched last (diagnostic of CTA-to-CTA skew): [i][linear block id], i = 0 main loop done, 1 drained,
+// 2 stores read, 3 exit
+__device__ __forceinline__ unsigned smid_() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ unsigned long long g_cta_clock[10][1024];  // [4] first operands landed, [5] SM id, [6] entry, [7] prologue done, [8] dependency resolved
+__device__ int g_cta_slot = 5;                        // which kernel of the step records per-CTA marks (annf_debug_cta_clocks sets it)
+__device__ unsigned long long g_sm_exit[8][256];      // [kernel slot][SM id]: when the (last) CTA of that kernel left that SM
+#define ANNF_TCTA(i) do { const unsigned b_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (b_ < 1024 && p.dbg == g_cta_slot) { g_cta_clock[i][b_] = gtimer(); g_cta_clock[5][b_] = smid_(); } } while (0)
+#define ANNF_TSM_EXIT(slot) do { if ((slot) >= 0 && (slot) < 8) g_sm_exit[slot][smid_() & 255] = gtimer(); } while (0)
+// start-up of one LATE CTA of the force GEMM (block (20, 0): launched when the GEMM before it leaves the SM), into slot 7:
+// 0 entry, 1 barriers initialised, 2 TMEM allocated, 3 static vectors loaded, 4 CTA / pair synchronised, 5 B requested,
+// 6 dependency resolved, 7 A requested, 8 first operands landed
+#define ANNF_TLATE(i) do { if (p.dbg == 5 && blockIdx.x == 20 && blockIdx.y == 0) g_tensor_clock[7][i] = gtimer(); } while (0)
 #define ANNF_TWAIT_BEGIN() const long long tw_ = clock64()
 #define ANNF_TWAIT_END(slot, i) do { if ((slot) >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tensor_clock[slot][i] += (unsigned long long) (clock64() - tw_); } while (0)
 #else
 #define ANNF_TWAIT_BEGIN() do { } while (0)
 #define ANNF_TWAIT_END(slot, i) do { } while (0)
 #define ANNF_TMARK(slot, i) do { } while (0)
+#define ANNF_TCTA(i) do { } while (0)
+#define ANNF_TSM_EXIT(slot) do { } while (0)
+#define ANNF_TLATE(i) do { } while (0)
 #define ANNF_TGRID_START(slot) do { } while (0)
 #define ANNF_TGRID_END(slot) do { } while (0)
 #endif
@@ -628,7 +643,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const bool direct = p.direct_store != 0;                // unsplit force GEMM: registers -> swizzled tile -> TMA store
 
     ANNF_TGRID_START(p.dbg);
-    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 0);
+    if (threadIdx.x == 0) { ANNF_TMARK(p.dbg, 0); ANNF_TCTA(6); ANNF_TLATE(0); }
     pdl_launch_dependents();                                // the next kernel may start its own prologue now
     if (p.dry & 1) return;
     if (warp == kEpiWarps && lane == 0) {
@@ -642,6 +657,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             mbar_init(smem_u32(&bar_acc_empty[b]), CG * kEpiWarps);   // one arrival per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ANNF_TLATE(1);
     }
     if (warp == kEpiWarps + 1) {
         if (CG == 2) {
@@ -651,21 +667,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t) (NB * BN)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
-    }
-    if (warp == kEpiWarps + 2) {
-        // static per-tile vectors (weights' scale exponents, biases): not produced by an earlier kernel of the step
-        for (int c = lane; c < BN; c += 32) {
-            const int n = n0 + c;
-            s_b_exp[c] = (KIND == KIND_F16 && n < p.N) ? __ldg(p.b_exp + n) : 0;
-            s_bias[c] = ((p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR) && n < p.N) ? __ldg(p.bias + n) : 0.f;
-        }
+        if (lane == 0) ANNF_TLATE(2);
     }
     tcgen05_fence_before();
     if (CX == 2) cg::this_cluster().sync();                 // the peer arrives on / multicasts into this CTA: its barriers must exist first
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 1);
+    if (threadIdx.x == 0) { ANNF_TMARK(p.dbg, 1); ANNF_TCTA(7); ANNF_TLATE(4); }
     // One pipeline stage of K-block i: arm the stage's barrier, load the A rows (activations: written by the kernel before this
     // one) and / or the B rows (weights: static).  Called by the producer thread only.
     constexpr bool kHintA = (kL2Hints & 4) != 0, kHintB = (kL2Hints & 8) != 0;
@@ -717,10 +726,30 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     // The weights do not depend on the kernel before this one: the first stages are armed and their B halves requested BEFORE the
     // dependency wait, so that after it only the A halves are still on their way (the wait-to-first-MMA gap was 1.6 - 1.9 us).
     const int npre = (p.dry || p.no_b_prefetch) ? 0 : min(kStages, num_kb);
-    if (warp == kEpiWarps && lane == 0)
+    if (warp == kEpiWarps && lane == 0) {
         for (int i = 0; i < npre; i++) issue_stage(i, false, true, true);
+        ANNF_TLATE(5);
+    }
+    if (warp == kEpiWarps + 2) {
+        // static per-tile vectors (weights' scale exponents, biases): not produced by an earlier kernel of the step.  AFTER the
+        // prologue rendezvous, and all loads in flight at once: as a rolled loop before it, these were BN / 32 dependent L2 round
+        // trips (2.9 us at BN = 256) that every warp of a CTA launched late — on an SM the previous GEMM had just left — sat out
+        // before its first TMA request (profiles/r02_cta_startup.md).
+        int be[BN / 32];
+        float bi[BN / 32];
+        const bool has_bias = p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_LINEAR;
+#pragma unroll
+        for (int j = 0; j < BN / 32; j++) {
+            const int n = n0 + lane + 32 * j;
+            be[j] = (KIND == KIND_F16 && n < p.N) ? __ldg(p.b_exp + n) : 0;
+            bi[j] = (has_bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < BN / 32; j++) { s_b_exp[lane + 32 * j] = be[j]; s_bias[lane + 32 * j] = bi[j]; }
+        if (lane == 0) ANNF_TLATE(3);
+    }
     pdl_wait();                                             // everything below reads what earlier kernels wrote
-    if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 2);
+    if (threadIdx.x == 0) { ANNF_TMARK(p.dbg, 2); ANNF_TCTA(8); ANNF_TLATE(6); }
     if (warp == kEpiWarps + 2) {
         // per-row scale exponents written by earlier kernels of the step; published to the epilogue by named barrier 1
         if (KIND == KIND_F16) {
@@ -793,6 +822,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     if (i < npre) {                                               // armed, and its B half issued, before the dependency wait
                         if (i == 0) ANNF_TMARK(p.dbg, 3);
                         issue_stage(i, true, false, false);
+                        if (i == 0) ANNF_TLATE(7);
                         continue;
                     }
                     const int s = i % kStages;
@@ -834,7 +864,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                         mbar_wait(smem_u32(&bar_full[s]), ph);                     // TMA bytes landed (both CTAs)
                         ANNF_TWAIT_END(p.dbg, 20); }
                         tcgen05_fence_after();
-                        if (i == 0) ANNF_TMARK(p.dbg, 4);
+                        if (i == 0) { ANNF_TMARK(p.dbg, 4); ANNF_TCTA(4); ANNF_TLATE(8); }
                         const uint32_t base = smem_u32(data + (size_t) s * Cfg::kStageBytes);
                         const uint32_t a_hi = base, a_lo = base + BM * kBlockBytes;
                         const uint32_t b_hi = base + 2 * BM * kBlockBytes, b_lo = b_hi + kBRows * kBlockBytes;
@@ -863,6 +893,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                     else umma_commit(smem_u32(&bar_acc_full[buf]));
                 }
                 ANNF_TMARK(p.dbg, 5);
+                ANNF_TCTA(0);
             }
         }
         if (BN >= 256) finish_tile(false);
@@ -898,7 +929,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
             }
         }
-        if (threadIdx.x == 0) ANNF_TMARK(p.dbg, 6);
+        if (threadIdx.x == 0) { ANNF_TMARK(p.dbg, 6); ANNF_TCTA(1); }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + 1)) : "memory");    // the staged per-tile vectors are in place
         if (S == 1 && direct) {
             // Unsplit force GEMM writing whole rows: every thread turns its own accumulators into forces (x 2^-(e_row + e_col)),
@@ -929,6 +960,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
                 ANNF_TMARK(p.dbg, 13);
                 tma_store_commit_and_wait_read();                                  // shared memory has been read: the CTA may leave
                 ANNF_TMARK(p.dbg, 14);
+                ANNF_TCTA(2);
             }
         } else {
             // park the tile in shared memory (all TMA loads have landed and been consumed: the stage buffers are free).
@@ -949,6 +981,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (NB * BN)) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) (NB * BN)) : "memory");
     }
+    if (threadIdx.x == 0) { ANNF_TCTA(3); ANNF_TSM_EXIT(p.dbg); }
     ANNF_TGRID_END(p.dbg);
 }
 
@@ -2672,3 +2705,18 @@ cudaError_t tensor_phase_clocks(unsigned long long* out192, bool reset) {
 }
 
 }  // namespace annf
+
+#ifdef ANNF_PHASE_CLOCKS
+// diagnostic build only, not part of the C-ABI: per-CTA marks of the last GEMM launched (tools/cta_skew.py)
+extern "C" __attribute__((visibility("default"))) int annf_debug_cta_clocks(long long* out6144, int next_slot) {
+    cudaDeviceSynchronize();
+    if (!out6144) {
+        static unsigned long long zeros[10 * 1024];
+        cudaMemcpyToSymbol(annf::g_cta_clock, zeros, sizeof(zeros));
+        return (int) cudaMemcpyToSymbol(annf::g_cta_slot, &next_slot, sizeof(int));
+    }
+    cudaError_t e = cudaMemcpyFromSymbol(out6144, annf::g_cta_clock, sizeof(unsigned long long) * 10 * 1024);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out6144 + 10 * 1024, annf::g_sm_exit, sizeof(unsigned long long) * 8 * 256);
+    return (int) e;
+}
+#endif
