@@ -126,7 +126,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-// L2 eviction priorities (compile-time: -DANNF_L2_HINTS=mask, default 7).  A step streams 18 MB of coordinates in and 18 MB of
+// L2 eviction priorities (compile-time: -DANNF_L2_HINTS=mask, default 15).  A step streams 18 MB of coordinates in and 18 MB of
 // forces out through an L2 that also has to keep 18 MB of weights and the 18 MB operand pair prep rewrites in place every step;
 // with default priorities the streams push those out (steady state, ncu --cache-control none: 13 MB of weights re-read from
 // DRAM and 15 MB of dead operand rows written back per step; profiles/r02_l2_hints.md).
@@ -135,7 +135,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // The unhinted instruction is used where a bit is off: a created evict_normal policy is NOT the default (hinting every access
 // "normal" cost the C5 step 4 us), and a run-time choice between the two forms cost 1.6 us (branches in prep's store loop).
 #ifndef ANNF_L2_HINTS
-#define ANNF_L2_HINTS 7
+#define ANNF_L2_HINTS 15
 #endif
 constexpr int kL2Hints = ANNF_L2_HINTS;
 __device__ __forceinline__ uint64_t l2_evict_first() {
@@ -754,12 +754,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
         // per-row scale exponents written by earlier kernels of the step; published to the epilogue by named barrier 1
         if (KIND == KIND_F16) {
             const bool has_out = p.epi != EPI_STORE && p.epi != EPI_FORCE;
-            for (int r = lane; r < BM; r += 32) {
-                const int m = m0 + r;
-                s_a_exp[r] = m < p.M ? p.a_exp[m] : 0;
-                s_out_exp[r] = (has_out && m < p.M) ? p.out_exp[m] : 0;
-                s_aux_exp[r] = (p.epi == EPI_TANH_GRAD && m < p.M) ? p.aux_exp[m] : 0;
+            int ea[BM / 32], eo[BM / 32], ex[BM / 32];      // all loads in flight at once (a short main loop ends 2.5 us after the wait)
+#pragma unroll
+            for (int j = 0; j < BM / 32; j++) {
+                const int m = m0 + lane + 32 * j;
+                ea[j] = m < p.M ? p.a_exp[m] : 0;
+                eo[j] = (has_out && m < p.M) ? p.out_exp[m] : 0;
+                ex[j] = (p.epi == EPI_TANH_GRAD && m < p.M) ? p.aux_exp[m] : 0;
             }
+#pragma unroll
+            for (int j = 0; j < BM / 32; j++) { s_a_exp[lane + 32 * j] = ea[j]; s_out_exp[lane + 32 * j] = eo[j]; s_aux_exp[lane + 32 * j] = ex[j]; }
         }
         __syncwarp();
         asm volatile("bar.arrive 1, %0;" ::"n"(32 * (kEpiWarps + 1)) : "memory");
