@@ -1572,14 +1572,33 @@ __global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int 
                 acc[u] = fma(w[u][1].y, (double) av[3], acc[u]);
             }
         }
+        // Eight warp-wide sums as ONE transposed butterfly: every round halves the values a lane carries (it keeps one half and
+        // sends the other to its partner), so 18 64-bit shuffles + 9 adds replace the 80 + 40 of eight separate butterflies
+        // (the shuffle unit was the busiest pipe of this kernel).  Lane l ends with the sum of output u = bits 4, 3, 2 of l.
+        {
+            double b4[4], b2[2];
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const double s = warp_sum(acc[u]);
-            if (lane == 0 && j0 + u < nL) part[warp][j0 + u] = s;
+            for (int i = 0; i < 4; i++) {
+                const double send = up16 ? acc[i] : acc[i + 4], keep = up16 ? acc[i + 4] : acc[i];
+                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double send = up8 ? b4[i] : b4[i + 2], keep = up8 ? b4[i + 2] : b4[i];
+                b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            const double send = up4 ? b2[0] : b2[1], keep = up4 ? b2[1] : b2[0];
+            double d = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            const int u = (lane >> 2) & 7;                  // bit 4 -> u bit 2, bit 3 -> u bit 1, bit 2 -> u bit 0
+            if ((lane & 3) == 0 && j0 + u < nL) part[warp][j0 + u] = d;
         }
     }
     for (int c = tid; c < net.num_center; c += kHeadThreads)
         cen[c] = centers ? (double) centers[(size_t) r * net.num_center + c] : net.center[c];
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 3);
     __syncthreads();
     if (tid < nL) zs[tid] = ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) + b[tid];
     __syncthreads();
@@ -1593,6 +1612,7 @@ __global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int 
     }
     if (tid < nL) dzf[tid] = (float) dzs[tid];
     __syncthreads();
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 4);
     const int hidden_type = net.types[L - 3];
     // KIND_F16: scale exponent of this replica's gradient rows, from a bound: |D[m]| <= max_j |dz_j| * max_m sum_j |W[j][m]|
     float d_scale = 1.f;
@@ -1610,6 +1630,7 @@ __global__ void __launch_bounds__(kHeadThreads, 7) head_kernel(NetView net, int 
             }
         }
     }
+    if (threadIdx.x == 0) ANNF_TMARK(dbg, 5);
     // the result is re-split to operand pairs: fp32 FMA is enough here.  Four consecutive hidden units per thread, vector loads.
     for (int m4 = 4 * tid; m4 < nH; m4 += 4 * kHeadThreads) {
         float av[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -2110,7 +2131,7 @@ struct TensorPlan {
     int chunk = kChunkDefault;                      // ANNF_TENSOR_CHUNK: K-blocks per TMEM accumulation chunk (accuracy experiments)
     bool no_cluster16 = false;                      // a 16-CTA cluster launch failed on this device
     int prep_mode = 0;                              // ANNF_PREP_MODE: 0 = bulk-copy kernel when the selection is contiguous (default); 1 = prep_kernel, coalesced walk; 2 = prep_kernel, 4-atom groups
-    int prep_warps = 4;                             // ANNF_PREP_WARPS: warps per replica of the bulk-copy kernel (1, 2, 4, 8)
+    int prep_warps = 8;                             // ANNF_PREP_WARPS: warps per replica of the bulk-copy kernel (1, 2, 4, 8)
     bool prep_pipelined = false;                    // ANNF_PREP_PIPELINED=0: the one-CTA-per-replica prep kernel (experiments)
     int prep_threads = 256;                         // CTA size of prep_kernel (ANNF_PREP_THREADS=128|256)
     int gsplit_mode = 0;                            // ANNF_GEMM_GSPLIT: 0 off (default), -1 auto, n > 1 forces n K ranges (split-K through global memory)

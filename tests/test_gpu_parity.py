@@ -550,7 +550,7 @@ def test_split_k_through_global_memory(splits, precision, monkeypatch):
 @pytest.mark.parametrize("atoms", [400, 404, 1500])
 def test_prep_kernel_flavours_agree(atoms, mode, precision, monkeypatch):
     """The ways the coordinate rows are centred, scaled and split (ANNF_PREP_MODE / ANNF_PREP_WARPS: 0 = one bulk copy per
-    replica into shared memory, 1 - 8 warps per replica — the default with 4; 1 = loads by 256 threads per replica, 16-byte
+    replica into shared memory, 1 - 8 warps per replica — the default with 8; 1 = loads by 256 threads per replica, 16-byte
     vectors with rotated statistics; 2 = the same kernel walking 4-atom groups) against the oracle, on a molecule 40 nm from
     the origin (the arithmetic is relative to the replica's first atom) and on row lengths that end a trip of the vector
     walk at different points."""

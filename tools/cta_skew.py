@@ -49,6 +49,8 @@ gx = 36 if slot == 5 else 4
 print("kernel slot", slot, "CTAs:", n, " (us on an arbitrary common axis; operands / main done: the MMA issuer lives in the even CTA of a pair)")
 for i, nm in cols:
     v = (t[i][t[i] > t0] - t0) / 1e3
+    if v.size == 0:
+        continue
     print("%-12s min %6.2f  p10 %6.2f  median %6.2f  p90 %6.2f  max %6.2f   (n=%d)" % (nm, v.min(), np.percentile(v, 10), np.median(v), np.percentile(v, 90), v.max(), v.size))
 print("per CTA: block (x, y) sm | previous GEMM left this SM | " + ", ".join(nm for _, nm in cols))
 for b in range(n):
