@@ -1,15 +1,17 @@
-// Layer-wise tensor-core path for wide networks (sm_100a): tcgen05.mma kind::tf32 with the 3xTF32
-// split, TMA-fed shared-memory pipeline, fp32 accumulators in TMEM, fused epilogues.
+// Layer-wise tensor-core path for wide networks (sm_100a): tcgen05.mma on operand PAIRS (kind::f16 on row-scaled fp16 pairs by
+// default, kind::tf32 on TF32 pairs selectable), TMA-fed shared-memory pipeline, fp32 accumulators in TMEM, fused epilogues.
 //
 // For a batch of R replicas the hidden layers are real dense contractions
 //     forward   X_{l+1} = act(X_l  * W_l^T + b_l)        M = R, N = n_{l+1}, K = n_l
 //     backward  D_l     = (D_{l+1} * W_l) (.) act'(X_l)   M = R, N = n_l,     K = n_{l+1}
 // (ANN_ReferenceKernels.cpp:193-209 and :340-354 with the replica index as the GEMM M dimension).
-// Every fp32 operand v is stored as a TF32 pair  hi = rna_tf32(v), lo = rna_tf32(v - hi)  so that
+// Every fp32 operand v is stored as a pair  hi = rn(v), lo = rn(v - hi)  (TF32, or fp16 of the value times a per-row power
+// of two: KindOf, ExpChain) so that
 //     v*w ~= hi_v*hi_w + hi_v*lo_w + lo_v*hi_w      (three tcgen05.mma per K-step, error ~2^-22)
 // Weights are split once at plan creation (both W and W^T, K-major for the tensor core); activations
 // are split by the epilogue that produces them.  The tiny output layer, the umbrella energy and its
-// gradient stay fp64 in a SIMT "head" kernel; gather/centre ("prep") is a bandwidth-bound SIMT kernel;
+// gradient stay fp64 in a SIMT "head" kernel; gather/centre ("prep": prep_bulk_kernel for a contiguous selection — one bulk
+// copy per replica row — prep_kernel otherwise) is a bandwidth-bound SIMT kernel;
 // the Jacobian of "divide by s, subtract the centroid" is folded into the backward copy of the first connection at plan
 // creation, so the last backward contraction's accumulator is the force and its epilogue writes it straight out.
 //
